@@ -55,7 +55,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (globaltimer_ns() - t0 > PK_WAIT_TIMEOUT_NS) {

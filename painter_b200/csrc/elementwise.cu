@@ -1,0 +1,600 @@
+// painter_b200 — bandwidth-bound kernels of the hot path (LayerNorm, token assembly, layout/cast
+// helpers, reductions).  All are warp-shuffle / 128-bit vectorised HBM streamers; none needs tensor cores.
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/painter_b200.h"
+
+namespace pk {
+
+// =============================================================================================
+// LayerNorm over the channel dim (nn.LayerNorm(eps=1e-6), models_painter.py:193,200,315)
+// one warp per row; row kept in registers (C <= 1024, C % 128 == 0); two-pass variance.
+// =============================================================================================
+constexpr int LN_MAX_V4 = 8;   // C <= 1024
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, OutT* __restrict__ out, int ldo,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nv = C / 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+  float4 v[LN_MAX_V4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      v[i] = xr[i * 32 + lane];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  OutT* orow = out + static_cast<size_t>(row) * ldo;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+      const float y0 = (v[i].x - mean) * rstd * g.x + b.x;
+      const float y1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float y2 = (v[i].z - mean) * rstd * g.z + b.z;
+      const float y3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(OutT) == 2) {
+        uint2 u;
+        u.x = pack_bf16x2(y0, y1);
+        u.y = pack_bf16x2(y2, y3);
+        reinterpret_cast<uint2*>(orow)[i * 32 + lane] = u;
+      } else {
+        reinterpret_cast<float4*>(orow)[i * 32 + lane] = make_float4(y0, y1, y2, y3);
+      }
+    }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ dres);  dgamma += dy*xhat; dbeta += dy
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+              const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C) {
+  extern __shared__ float red[];  // [8 warps][2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = C / 128;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 gam[LN_MAX_V4], ag[LN_MAX_V4], ab[LN_MAX_V4];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      gam[i] = __ldg(g4 + i * 32 + lane);
+      ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  const float invC = 1.0f / C;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * lddy);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[LN_MAX_V4], gd[LN_MAX_V4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i)
+      if (i < nv) {
+        const float4 xv = xr[i * 32 + lane], dv = dr[i * 32 + lane];
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        gd[i] = make_float4(dv.x * gam[i].x, dv.y * gam[i].y, dv.z * gam[i].z, dv.w * gam[i].w);
+        s1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
+        s2 += (gd[i].x * xh[i].x + gd[i].y * xh[i].y) + (gd[i].z * xh[i].z + gd[i].w * xh[i].w);
+        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y;
+        ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      }
+    const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+    float4* dxr = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * C);
+    const float4* rr =
+        dres ? reinterpret_cast<const float4*>(dres + static_cast<size_t>(row) * C) : nullptr;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i)
+      if (i < nv) {
+        float4 o = make_float4(rs * (gd[i].x - c1 - xh[i].x * c2), rs * (gd[i].y - c1 - xh[i].y * c2),
+                               rs * (gd[i].z - c1 - xh[i].z * c2), rs * (gd[i].w - c1 - xh[i].w * c2));
+        if (rr) {
+          const float4 r = rr[i * 32 + lane];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        dxr[i * 32 + lane] = o;
+      }
+  }
+  // block reduce of dgamma/dbeta partials, then one atomic per column per block
+  float4* sg = reinterpret_cast<float4*>(red) + static_cast<size_t>(warp) * 2 * (C / 4);
+  float4* sb = sg + C / 4;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i)
+    if (i < nv) {
+      sg[i * 32 + lane] = ag[i];
+      sb[i * 32 + lane] = ab[i];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[static_cast<size_t>(w) * 2 * C + c];
+    if (c < C) atomicAdd(dgamma + c, s);
+    else atomicAdd(dbeta + (c - C), s);
+  }
+}
+
+// =============================================================================================
+// PatchEmbed lowering: stride-16 conv == GEMM over (c, r, s)-ordered patch rows
+// (vitdet_utils.py:178-186, models_painter.py:387-388).  Both images (imgs | tgts) in one launch.
+// out[(img*N + i*w + j), (c*p + r)*p + s] = bf16(src[img][c][i*p + r][j*p + s])
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+im2col_patch_kernel(const float* __restrict__ imgs, const float* __restrict__ tgts,
+                    __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W, int p) {
+  const int h = H / p, w = W / p, N = h * w;
+  const int kdim = Cin * p * p;
+  const int chunks = kdim / 8;
+  const size_t total = static_cast<size_t>(2 * B) * N * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(idx % chunks);
+    const size_t row = idx / chunks;
+    const int img = static_cast<int>(row / N), t = static_cast<int>(row % N);
+    const int i = t / w, j = t % w;
+    const int k0 = ch * 8;
+    const int c = k0 / (p * p), rem = k0 % (p * p), r = rem / p, s0 = rem % p;
+    const float* src = (img < B ? imgs + static_cast<size_t>(img) * Cin * H * W
+                                : tgts + static_cast<size_t>(img - B) * Cin * H * W) +
+                       (static_cast<size_t>(c) * H + i * p + r) * W + j * p + s0;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + row * kdim + k0) = u;
+  }
+}
+
+// =============================================================================================
+// Token assembly (models_painter.py:392-409; SegGPT type tokens models_seggpt.py:414-420)
+//   x rows: E + seg_x + P (+ type);   y rows: (E*(1-m) + mask_token*m) + seg_y + P (+ type)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+assemble_kernel(const float* __restrict__ E, const uint8_t* __restrict__ mask, int maskB,
+                const float* __restrict__ mask_token, const float* __restrict__ seg_x,
+                const float* __restrict__ seg_y, const float* __restrict__ pos,
+                const float* __restrict__ type_emb, float* __restrict__ out, int B, int N, int C) {
+  const int c4n = C / 4;
+  const size_t total = static_cast<size_t>(2 * B) * N * c4n;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(idx % c4n);
+    const size_t row = idx / c4n;
+    const int img = static_cast<int>(row / N), n = static_cast<int>(row % N);
+    const bool isY = img >= B;
+    const int b = isY ? img - B : img;
+    float4 e = reinterpret_cast<const float4*>(E)[idx];
+    if (isY) {
+      const float m = mask[static_cast<size_t>(b % maskB) * N + n] ? 1.f : 0.f;
+      const float4 mt = __ldg(reinterpret_cast<const float4*>(mask_token) + c4);
+      e.x = e.x * (1.f - m) + mt.x * m; e.y = e.y * (1.f - m) + mt.y * m;
+      e.z = e.z * (1.f - m) + mt.z * m; e.w = e.w * (1.f - m) + mt.w * m;
+    }
+    const float4 sg = __ldg(reinterpret_cast<const float4*>(isY ? seg_y : seg_x) + c4);
+    const float4 ps = __ldg(reinterpret_cast<const float4*>(pos) + static_cast<size_t>(n) * c4n + c4);
+    e.x = (e.x + sg.x) + ps.x; e.y = (e.y + sg.y) + ps.y;
+    e.z = (e.z + sg.z) + ps.z; e.w = (e.w + sg.w) + ps.w;
+    if (type_emb) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(type_emb) + static_cast<size_t>(b) * c4n + c4);
+      e.x += t.x; e.y += t.y; e.z += t.z; e.w += t.w;
+    }
+    reinterpret_cast<float4*>(out)[idx] = e;
+  }
+}
+
+// backward of the assembly: dE (bf16, y rows gated by 1-m), dpos[N,C], dseg_x, dseg_y, dmask_token
+// block = (C/4, TY) threads, one token per threadIdx.y
+__global__ void assemble_bwd_kernel(const float* __restrict__ dZ, const uint8_t* __restrict__ mask,
+                                    int maskB, __nv_bfloat16* __restrict__ dE, float* __restrict__ dpos,
+                                    float* __restrict__ dseg_x, float* __restrict__ dseg_y,
+                                    float* __restrict__ dmask_token, int B, int N, int C) {
+  extern __shared__ float4 sred[];  // [3][TY][C/4]
+  const int c4n = C / 4;
+  const int c4 = threadIdx.x;
+  const int n = blockIdx.x * blockDim.y + threadIdx.y;
+  float4 sx = make_float4(0, 0, 0, 0), sy = sx, sm = sx;
+  if (n < N) {
+    for (int img = 0; img < 2 * B; ++img) {
+      const size_t off = (static_cast<size_t>(img) * N + n) * c4n + c4;
+      float4 d = reinterpret_cast<const float4*>(dZ)[off];
+      if (img < B) {
+        sx.x += d.x; sx.y += d.y; sx.z += d.z; sx.w += d.w;
+      } else {
+        sy.x += d.x; sy.y += d.y; sy.z += d.z; sy.w += d.w;
+        if (mask[static_cast<size_t>((img - B) % maskB) * N + n]) {
+          sm.x += d.x; sm.y += d.y; sm.z += d.z; sm.w += d.w;
+          d = make_float4(0, 0, 0, 0);
+        }
+      }
+      uint2 u;
+      u.x = pack_bf16x2(d.x, d.y);
+      u.y = pack_bf16x2(d.z, d.w);
+      reinterpret_cast<uint2*>(dE)[off] = u;
+    }
+    reinterpret_cast<float4*>(dpos)[static_cast<size_t>(n) * c4n + c4] =
+        make_float4(sx.x + sy.x, sx.y + sy.y, sx.z + sy.z, sx.w + sy.w);
+  }
+  const int TY = blockDim.y;
+  sred[(0 * TY + threadIdx.y) * c4n + c4] = sx;
+  sred[(1 * TY + threadIdx.y) * c4n + c4] = sy;
+  sred[(2 * TY + threadIdx.y) * c4n + c4] = sm;
+  __syncthreads();
+  if (threadIdx.y < 3) {
+    const int which = threadIdx.y;
+    float4 s = make_float4(0, 0, 0, 0);
+    for (int t = 0; t < TY; ++t) {
+      const float4 v = sred[(which * TY + t) * c4n + c4];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* dst = (which == 0 ? dseg_x : (which == 1 ? dseg_y : dmask_token)) + c4 * 4;
+    atomicAdd(dst + 0, s.x); atomicAdd(dst + 1, s.y); atomicAdd(dst + 2, s.z); atomicAdd(dst + 3, s.w);
+  }
+}
+
+// =============================================================================================
+// Bicubic resize of the absolute position table (get_abs_pos, vitdet_utils.py:141-157):
+// F.interpolate(mode="bicubic", align_corners=False), A = -0.75, border-clamped taps.  NHWC [s,s,C]->[h,w,C]
+// =============================================================================================
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+template <bool BWD>
+__global__ void bicubic_kernel(const float* __restrict__ src, float* __restrict__ dst, int sh, int sw,
+                               int h, int w, int C) {
+  // FWD: src [sh,sw,C] -> dst [h,w,C].   BWD: src = d(dst) [h,w,C], dst = d(src) [sh,sw,C] (atomic)
+  const size_t total = static_cast<size_t>(h) * w * C;
+  const float scale_h = static_cast<float>(sh) / h, scale_w = static_cast<float>(sw) / w;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const int j = static_cast<int>((idx / C) % w), i = static_cast<int>(idx / (static_cast<size_t>(C) * w));
+    const float ry = scale_h * (i + 0.5f) - 0.5f, rx = scale_w * (j + 0.5f) - 0.5f;
+    const float fy = floorf(ry), fx = floorf(rx);
+    float wy[4], wx[4];
+    cubic_coeffs(ry - fy, wy);
+    cubic_coeffs(rx - fx, wx);
+    const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+    float acc = 0.f;
+    const float g = BWD ? src[idx] : 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), sh - 1);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), sw - 1);
+        const size_t so = (static_cast<size_t>(yy) * sw + xx) * C + c;
+        if (BWD) atomicAdd(dst + so, g * wy[a] * wx[b]);
+        else acc += src[so] * wy[a] * wx[b];
+      }
+    }
+    if (!BWD) dst[idx] = acc;
+  }
+}
+
+// =============================================================================================
+// Early merge (models_painter.py:414-415): out = 0.5 * (z[:half] + z[half:]);  bwd: both halves = 0.5 * d
+// =============================================================================================
+__global__ void merge_halves_kernel(const float4* __restrict__ z, float4* __restrict__ out, size_t half4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < half4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 a = z[i], b = z[i + half4];
+    out[i] = make_float4((a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f, (a.w + b.w) * 0.5f);
+  }
+}
+__global__ void merge_halves_bwd_kernel(const float4* __restrict__ d, float4* __restrict__ out, size_t half4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < half4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 a = d[i];
+    const float4 o = make_float4(a.x * 0.5f, a.y * 0.5f, a.z * 0.5f, a.w * 0.5f);
+    out[i] = o;
+    out[i + half4] = o;
+  }
+}
+
+// =============================================================================================
+// fp32 -> bf16 cast (weights each step; gradients entering a GEMM), optional per-row-group scale
+// (DropPath backward) and optional fused column sum (bias gradient).
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = in[i];
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    out[i] = u;
+  }
+}
+
+// in f32 [M, C] (ld = ldin) -> out bf16 [M, C] scaled by rowscale[row / rows_per_group];
+// colsum[c] += sum_rows(scaled value).  block (C/4 <= 256 threads x), rows strided by gridDim.
+__global__ void scale_cast_colsum_kernel(const float* __restrict__ in, int ldin,
+                                         const float* __restrict__ rowscale, int rows_per_group,
+                                         __nv_bfloat16* __restrict__ out, float* __restrict__ colsum,
+                                         int M, int C) {
+  const int c4n = C / 4;
+  for (int c4 = threadIdx.x; c4 < c4n; c4 += blockDim.x) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int row = blockIdx.x; row < M; row += gridDim.x) {
+      const float sc = rowscale ? rowscale[row / rows_per_group] : 1.f;
+      float4 v = reinterpret_cast<const float4*>(in + static_cast<size_t>(row) * ldin)[c4];
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C)[c4] = u;
+    }
+    if (colsum) {
+      atomicAdd(colsum + c4 * 4 + 0, acc.x); atomicAdd(colsum + c4 * 4 + 1, acc.y);
+      atomicAdd(colsum + c4 * 4 + 2, acc.z); atomicAdd(colsum + c4 * 4 + 3, acc.w);
+    }
+  }
+}
+
+// colsum[c] += sum_m in[m, c]   (bf16 in, ld = ldin);  grid (ceil(C/256), row chunks)
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, int ldin, float* __restrict__ colsum, int M,
+                   int C, int rows_per_block) {
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    for (int row = r0 + warp; row < r1; row += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * ldin + c0);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        acc[2 * t] += __uint_as_float(w[t] << 16);
+        acc[2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) red[warp][lane * 8 + t] = acc[t];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(colsum + c, s);
+  }
+}
+
+// =============================================================================================
+// SegGPT feature ensemble + residual (models_seggpt.py:220-231 then :233):
+//   out = z + (top-half rows: a ; bottom-half rows: mean of a over the members of the prompt group)
+// a, z, out: [G*P, N, C] with G groups (2 before the early merge, 1 after)
+// =============================================================================================
+__global__ void ensemble_resid_kernel(const float4* __restrict__ a, const float4* __restrict__ z,
+                                      float4* __restrict__ out, int G, int P, int N, int C4) {
+  const size_t per_img = static_cast<size_t>(N) * C4;
+  const size_t total = static_cast<size_t>(G) * per_img;
+  const float inv = 1.0f / P;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx / per_img);
+    const size_t r = idx % per_img;
+    const int n = static_cast<int>(r / C4);
+    const size_t base = static_cast<size_t>(g) * P * per_img + r;
+    if (n < N / 2) {
+      for (int p = 0; p < P; ++p) {
+        const float4 av = a[base + p * per_img], zv = z[base + p * per_img];
+        out[base + p * per_img] = make_float4(zv.x + av.x, zv.y + av.y, zv.z + av.z, zv.w + av.w);
+      }
+    } else {
+      float4 s = make_float4(0, 0, 0, 0);
+      for (int p = 0; p < P; ++p) {
+        const float4 av = a[base + p * per_img];
+        s.x += av.x; s.y += av.y; s.z += av.z; s.w += av.w;
+      }
+      s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+      for (int p = 0; p < P; ++p) {
+        const float4 zv = z[base + p * per_img];
+        out[base + p * per_img] = make_float4(zv.x + s.x, zv.y + s.y, zv.z + s.z, zv.w + s.w);
+      }
+    }
+  }
+}
+
+static inline int grid_for(size_t work_items, int block) {
+  size_t g = (work_items + block - 1) / block;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace pk
+
+using namespace pk;
+
+extern "C" int pk_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, float eps,
+                                void* out, int ldo, int out_is_bf16, float* mean, float* rstd, int M,
+                                int C, void* stream) {
+  PK_CHECK(x && gamma && beta && out, "pk_layernorm_fwd: null pointer");
+  PK_CHECK(C % 128 == 0 && C <= 128 * LN_MAX_V4, "pk_layernorm_fwd: C=%d must be a multiple of 128, <= %d", C,
+           128 * LN_MAX_V4);
+  PK_CHECK(ldx % 4 == 0 && ldo % 4 == 0, "pk_layernorm_fwd: strides must be multiples of 4");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (M + 7) / 8;
+  if (out_is_bf16)
+    ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps,
+                                                      static_cast<__nv_bfloat16*>(out), ldo, mean, rstd, M, C);
+  else
+    ln_fwd_kernel<float><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<float*>(out), ldo,
+                                              mean, rstd, M, C);
+  PK_LAUNCH_CHECK("pk_layernorm_fwd");
+  return 0;
+}
+
+extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* mean,
+                                const float* rstd, const float* gamma, const float* dres, float* dx,
+                                float* dgamma, float* dbeta, int M, int C, void* stream) {
+  PK_CHECK(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "pk_layernorm_bwd: null pointer");
+  PK_CHECK(C % 128 == 0 && C <= 128 * LN_MAX_V4, "pk_layernorm_bwd: bad C=%d", C);
+  const size_t smem = static_cast<size_t>(8) * 2 * C * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
+    attr = true;
+  }
+  int grid = sm_count() * 2;
+  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
+  ln_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, mean, rstd, gamma,
+                                                                      dres, dx, dgamma, dbeta, M, C);
+  PK_LAUNCH_CHECK("pk_layernorm_bwd");
+  return 0;
+}
+
+extern "C" int pk_im2col_patch(const float* imgs, const float* tgts, void* out_bf16, int B, int Cin, int H,
+                               int W, int p, void* stream) {
+  PK_CHECK(imgs && tgts && out_bf16, "pk_im2col_patch: null pointer");
+  PK_CHECK(p % 8 == 0 && H % p == 0 && W % p == 0 && W % 4 == 0, "pk_im2col_patch: bad geometry");
+  const size_t total = static_cast<size_t>(2 * B) * (H / p) * (W / p) * (Cin * p * p / 8);
+  im2col_patch_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      imgs, tgts, static_cast<__nv_bfloat16*>(out_bf16), B, Cin, H, W, p);
+  PK_LAUNCH_CHECK("pk_im2col_patch");
+  return 0;
+}
+
+extern "C" int pk_assemble_tokens(const float* E, const uint8_t* mask, int maskB, const float* mask_token,
+                                  const float* seg_x, const float* seg_y, const float* pos,
+                                  const float* type_emb, float* out, int B, int N, int C, void* stream) {
+  PK_CHECK(E && mask && mask_token && seg_x && seg_y && pos && out, "pk_assemble_tokens: null pointer");
+  PK_CHECK(C % 4 == 0 && maskB >= 1, "pk_assemble_tokens: bad shape");
+  const size_t total = static_cast<size_t>(2 * B) * N * (C / 4);
+  assemble_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      E, mask, maskB, mask_token, seg_x, seg_y, pos, type_emb, out, B, N, C);
+  PK_LAUNCH_CHECK("pk_assemble_tokens");
+  return 0;
+}
+
+extern "C" int pk_assemble_tokens_bwd(const float* dZ, const uint8_t* mask, int maskB, void* dE_bf16,
+                                      float* dpos, float* dseg_x, float* dseg_y, float* dmask_token, int B,
+                                      int N, int C, void* stream) {
+  PK_CHECK(dZ && mask && dE_bf16 && dpos && dseg_x && dseg_y && dmask_token,
+           "pk_assemble_tokens_bwd: null pointer");
+  PK_CHECK(C % 4 == 0 && C / 4 <= 256, "pk_assemble_tokens_bwd: C=%d unsupported", C);
+  const int tx = C / 4;
+  int ty = 1024 / tx;
+  if (ty > 8) ty = 8;
+  if (ty < 3) ty = 3;
+  PK_CHECK(tx * ty <= 1024, "pk_assemble_tokens_bwd: C too large");
+  const size_t smem = static_cast<size_t>(3) * ty * tx * sizeof(float4);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(assemble_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * 256 * 16);
+    attr = true;
+  }
+  assemble_bwd_kernel<<<(N + ty - 1) / ty, dim3(tx, ty), smem, static_cast<cudaStream_t>(stream)>>>(
+      dZ, mask, maskB, static_cast<__nv_bfloat16*>(dE_bf16), dpos, dseg_x, dseg_y, dmask_token, B, N, C);
+  PK_LAUNCH_CHECK("pk_assemble_tokens_bwd");
+  return 0;
+}
+
+extern "C" int pk_bicubic_fwd(const float* src, float* dst, int sh, int sw, int h, int w, int C, void* stream) {
+  PK_CHECK(src && dst, "pk_bicubic_fwd: null pointer");
+  bicubic_kernel<false><<<grid_for(static_cast<size_t>(h) * w * C, 256), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(src, dst, sh, sw, h, w, C);
+  PK_LAUNCH_CHECK("pk_bicubic_fwd");
+  return 0;
+}
+extern "C" int pk_bicubic_bwd(const float* ddst, float* dsrc_accum, int sh, int sw, int h, int w, int C,
+                              void* stream) {
+  PK_CHECK(ddst && dsrc_accum, "pk_bicubic_bwd: null pointer");
+  bicubic_kernel<true><<<grid_for(static_cast<size_t>(h) * w * C, 256), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(ddst, dsrc_accum, sh, sw, h, w, C);
+  PK_LAUNCH_CHECK("pk_bicubic_bwd");
+  return 0;
+}
+
+extern "C" int pk_merge_halves(const float* z, float* out, long long half_elems, void* stream) {
+  PK_CHECK(z && out && half_elems % 4 == 0, "pk_merge_halves: bad args");
+  merge_halves_kernel<<<grid_for(half_elems / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(z), reinterpret_cast<float4*>(out), half_elems / 4);
+  PK_LAUNCH_CHECK("pk_merge_halves");
+  return 0;
+}
+extern "C" int pk_merge_halves_bwd(const float* d, float* out, long long half_elems, void* stream) {
+  PK_CHECK(d && out && half_elems % 4 == 0, "pk_merge_halves_bwd: bad args");
+  merge_halves_bwd_kernel<<<grid_for(half_elems / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(d), reinterpret_cast<float4*>(out), half_elems / 4);
+  PK_LAUNCH_CHECK("pk_merge_halves_bwd");
+  return 0;
+}
+
+extern "C" int pk_cast_bf16(const float* in, void* out_bf16, long long n, void* stream) {
+  PK_CHECK(in && out_bf16 && n % 4 == 0, "pk_cast_bf16: bad args (n must be a multiple of 4)");
+  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out_bf16), n / 4);
+  PK_LAUNCH_CHECK("pk_cast_bf16");
+  return 0;
+}
+
+extern "C" int pk_scale_cast_colsum(const float* in, int ldin, const float* rowscale, int rows_per_group,
+                                    void* out_bf16, float* colsum, int M, int C, void* stream) {
+  PK_CHECK(in && out_bf16 && C % 4 == 0 && ldin % 4 == 0, "pk_scale_cast_colsum: bad args");
+  if (rowscale) PK_CHECK(rows_per_group > 0, "pk_scale_cast_colsum: rows_per_group must be > 0");
+  int tx = C / 4;
+  if (tx > 256) tx = 256;
+  int grid = sm_count() * 4;
+  if (grid > M) grid = M;
+  scale_cast_colsum_kernel<<<grid, tx, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ldin, rowscale, rows_per_group, static_cast<__nv_bfloat16*>(out_bf16), colsum, M, C);
+  PK_LAUNCH_CHECK("pk_scale_cast_colsum");
+  return 0;
+}
+
+extern "C" int pk_colsum_bf16(const void* in_bf16, int ldin, float* colsum, int M, int C, void* stream) {
+  PK_CHECK(in_bf16 && colsum && C % 8 == 0 && ldin % 8 == 0, "pk_colsum_bf16: bad args");
+  const int rpb = 256;
+  dim3 grid((C + 255) / 256, (M + rpb - 1) / rpb);
+  colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in_bf16), ldin, colsum, M, C, rpb);
+  PK_LAUNCH_CHECK("pk_colsum_bf16");
+  return 0;
+}
+
+extern "C" int pk_ensemble_resid(const float* a, const float* z, float* out, int G, int P, int N, int C,
+                                 void* stream) {
+  PK_CHECK(a && z && out && C % 4 == 0 && N % 2 == 0, "pk_ensemble_resid: bad args");
+  const size_t total = static_cast<size_t>(G) * N * (C / 4);
+  ensemble_resid_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(z), reinterpret_cast<float4*>(out),
+      G, P, N, C / 4);
+  PK_LAUNCH_CHECK("pk_ensemble_resid");
+  return 0;
+}

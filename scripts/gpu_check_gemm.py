@@ -70,12 +70,12 @@ def run_case(name, M, N, K, ta, tb, kind, bn):
         z = (ref + bias)
         want = (z, torch.nn.functional.gelu(z.bfloat16().float()))
     elif kind == "resid":
-        res = torch.randn(M, N, device=dev)
+        resid = torch.randn(M, N, device=dev)
         rpg = M // 4
         rs = torch.tensor([1.0, 0.0, 1.1, 0.9], device=dev)
-        fn = lambda: ops.gemm(a_in, b_in, trans_a=ta, trans_b=tb, kind=ops.EPI_RESID, bias=bias, aux=res,
+        fn = lambda: ops.gemm(a_in, b_in, trans_a=ta, trans_b=tb, kind=ops.EPI_RESID, bias=bias, aux=resid,
                               rowscale=rs, rows_per_group=rpg)
-        want = res + rs.repeat_interleave(rpg)[:, None] * (ref + bias)
+        want = resid + rs.repeat_interleave(rpg)[:, None] * (ref + bias)
     elif kind == "dgelu":
         z = torch.randn(M, N, device=dev).bfloat16()
         fn = lambda: ops.gemm(a_in, b_in, trans_a=ta, trans_b=tb, kind=ops.EPI_DGELU, aux=z)

@@ -1,0 +1,411 @@
+// painter_b200 — fused global attention forward with decomposed relative-position bias (sm_100a).
+//
+// Replaces models_painter.py:73-86 + util/vitdet_utils.py:63-125 (q*scale @ k^T, add_decomposed_rel_pos,
+// softmax, @ v) without ever materialising the [B*heads, N, N] score tensor.
+//
+// One CTA = 128 query tokens of one (batch, head); two CTAs co-reside per SM so one CTA's softmax
+// overlaps the other's tensor-core work.  6 warps:
+//   warp 0       TMA producer: Q tile, bf16 rel-pos tables, then K / V tiles (single-stage each)
+//   warp 1       MMA issuer (tcgen05, accumulators in TMEM): S = Q.K^T, O += P.V
+//   warps 2..5   softmax: one thread per query row (tcgen05.ld 32x32b), online softmax in the log2 domain
+//                with lazy rescaling, P written as bf16 into a 128B-swizzled smem tile for the P.V MMA
+// Key tiles are KT = 112 keys = R whole image rows (R = 112 / W) so that, inside a tile, the key's image
+// row / column are compile-time: rel_w lives in registers, rel_h needs R values per tile.
+// The bias itself comes from the tensor cores too: G_h = Q . T_h^T and G_w = Q . T_w^T (T = bf16 rel-pos
+// tables) are two extra MMAs at CTA start; rel_h[r, i] = G_h[r, i_r - i + h - 1] (Toeplitz gather).
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/painter_b200.h"
+
+namespace pk {
+
+constexpr int ATT_BM = 128;
+constexpr int ATT_KT = 112;
+constexpr int ATT_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr uint32_t ATT_SQ = 0;                 // 128 x 128 B
+constexpr uint32_t ATT_SK = 16384;             // 112 x 128 B
+constexpr uint32_t ATT_SV = ATT_SK + 14336;    // 112 x 128 B   (T_w staged here before the main loop)
+constexpr uint32_t ATT_SP = ATT_SV + 14336;    // 2 x (128 x 128 B) (T_h staged here before the main loop)
+constexpr uint32_t ATT_SRELH = ATT_SP + 32768; // 128 x (h+1) fp32  (>= 4 x 32 x 17 fp32 scratch)
+
+struct AttnFwdArgs {
+  int h, N, heads;
+  int th_pad, tw_pad;     // padded row counts of the bf16 tables (multiples of 16)
+  int relh_bytes;         // size of the sRelh region
+  float scale_log2;       // head_dim^-0.5 * log2(e)
+  __nv_bfloat16* out;     // [B*N, ldo]
+  int ldo;
+  float* lse;             // [B*heads, N]  (log2 domain: m + log2(l))
+};
+
+template <int W>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTw,
+                const AttnFwdArgs a) {
+  constexpr int R = ATT_KT / W;
+  static_assert(R * W == ATT_KT, "W must divide 112");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_base = smem_u32(smem_raw);
+  const uint32_t base = (raw_base + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_base);
+
+  const uint32_t sQ = base + ATT_SQ, sK = base + ATT_SK, sV = base + ATT_SV, sP = base + ATT_SP;
+  float* relh_gen = reinterpret_cast<float*>(gen + ATT_SRELH);
+  const uint32_t bar0 = base + ATT_SRELH + a.relh_bytes;
+  const uint32_t bar_q = bar0, bar_kf = bar0 + 8, bar_ke = bar0 + 16, bar_vf = bar0 + 24,
+                 bar_ve = bar0 + 32, bar_s = bar0 + 40, bar_p = bar0 + 48, bar_o = bar0 + 56,
+                 bar_g = bar0 + 64, bar_gr = bar0 + 72;
+  const uint32_t holder = bar0 + 80;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + ATT_SRELH + a.relh_bytes + 80);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int C = a.heads * 64;
+  const int num_tiles = (a.h + R - 1) / R;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmTh);
+    tma_prefetch_desc(&tmTw);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kf, 1);
+    mbar_init(bar_ke, 1);
+    mbar_init(bar_vf, 1);
+    mbar_init(bar_ve, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_g, 1);
+    mbar_init(bar_gr, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(holder, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *holder_gen;
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      mbar_expect_tx(bar_q, 16384u + static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u);
+      tma_load_3d(sQ, &tmQ, bar_q, head * 64, q0, b);
+      tma_load_2d(sP, &tmTh, bar_q, 0, 0);
+      tma_load_2d(sV, &tmTw, bar_q, 0, 0);
+      mbar_expect_tx(bar_kf, ATT_KT * 128);
+      tma_load_3d(sK, &tmKV, bar_kf, C + head * 64, 0, b);
+      mbar_wait(bar_g, 0);  // G_w MMA finished reading T_w out of the V buffer
+      mbar_expect_tx(bar_vf, ATT_KT * 128);
+      tma_load_3d(sV, &tmKV, bar_vf, 2 * C + head * 64, 0, b);
+      for (int j = 1; j < num_tiles; ++j) {
+        mbar_wait(bar_ke, (j - 1) & 1);
+        mbar_expect_tx(bar_kf, ATT_KT * 128);
+        tma_load_3d(sK, &tmKV, bar_kf, C + head * 64, j * ATT_KT, b);
+        mbar_wait(bar_ve, (j - 1) & 1);
+        mbar_expect_tx(bar_vf, ATT_KT * 128);
+        tma_load_3d(sV, &tmKV, bar_vf, 2 * C + head * 64, j * ATT_KT, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // -------------------------------------- MMA issuer --------------------------------------
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      {  // G_w = Q . T_w^T
+        const uint32_t idesc = make_idesc_bf16(128, a.tw_pad, false, false);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(bar_g);
+      }
+      mbar_wait(bar_gr, 0);
+      tc_fence_after();
+      {  // G_h = Q . T_h^T
+        const uint32_t idesc = make_idesc_bf16(128, a.th_pad, false, false);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sP + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(bar_g);
+      }
+      mbar_wait(bar_gr, 1);
+      tc_fence_after();
+      const uint32_t idesc_qk = make_idesc_bf16(128, ATT_KT, false, false);
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+      for (int j = 0; j < num_tiles; ++j) {
+        mbar_wait(bar_kf, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sK + k * 32, 16, 1024), idesc_qk, k != 0);
+        umma_commit(bar_ke);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, j & 1);
+        mbar_wait(bar_vf, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < ATT_KT / 16; ++kk)
+          umma_ss(tO, make_sdesc(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                  make_sdesc(sV + kk * 2048, 16, 1024), idesc_pv, (j | kk) != 0);
+        umma_commit(bar_ve);
+        if (j == num_tiles - 1) umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ------------------------------------ softmax warps ------------------------------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    int t = q0 + row;
+    const bool valid = t < a.N;
+    if (!valid) t = a.N - 1;
+    const int i_r = t / W, j_r = t - i_r * W;
+    const int h = a.h;
+    const int ldr = h + 1;
+    float* my_relh = relh_gen + static_cast<size_t>(row) * ldr;
+
+    // ---- rel_w -> registers (through a private smem scratch row for the dynamic shift) ----
+    float relw[W];
+    {
+      float* scratch = relh_gen + (static_cast<size_t>(quarter) * 32 + lane) * 17;
+      mbar_wait(bar_g, 0);
+      tc_fence_after();
+      for (int c0 = 0; c0 < a.tw_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) scratch[c] = __uint_as_float(v[c]) * LOG2E;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const int tt = j_r + (W - 1) - j - c0;
+          if (tt >= 0 && tt < 16) relw[j] = scratch[tt];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive(bar_gr);
+    }
+    // ---- rel_h -> smem [row][h]  (Toeplitz gather: rel_h[i] = G_h[i_r - i + h - 1]) ----
+    {
+      mbar_wait(bar_g, 1);  // also implies every thread is done with the scratch rows (bar_gr phase 0)
+      tc_fence_after();
+      for (int c0 = 0; c0 < a.th_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int i = i_r + (h - 1) - (c0 + c);
+          if (i >= 0 && i < h) my_relh[i] = __uint_as_float(v[c]) * LOG2E;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive(bar_gr);
+    }
+
+    float m_ref = -INFINITY, l_sum = 0.f;
+    const float sc = a.scale_log2;
+    for (int j = 0; j < num_tiles; ++j) {
+      float hb[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = j * R + r;
+        hb[r] = my_relh[i < h ? i : h - 1];
+      }
+      const int keys_valid = (h - j * R) * W;  // >= ATT_KT except in a partial last tile
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      // ---------------- pass 1: row max of t = s*scale + bias (log2 domain) ----------------
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < ATT_KT; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int kc = c0 + c;
+          float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
+          if (kc >= keys_valid) tv = -INFINITY;
+          mx = fmaxf(mx, tv);
+        }
+      }
+      // ---------------- lazy rescale of the running state ----------------
+      const bool grow = mx > m_ref + 8.0f;
+      float alpha = 1.0f;
+      if (grow) {
+        alpha = exp2f(m_ref - mx);  // 0 on the first tile (m_ref = -inf)
+        l_sum *= alpha;
+        m_ref = mx;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t o[16];
+          tmem_ld_x16(tO + lane_addr + c0, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st_x16(tO + lane_addr + c0, o);
+        }
+        tmem_wait_st();
+      }
+      // ---------------- pass 2: p = exp2(t - m_ref), row sum, bf16 P tile into swizzled smem ----------------
+#pragma unroll
+      for (int c0 = 0; c0 < ATT_KT; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_wait_ld();
+        float p[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int kc = c0 + c;
+          float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
+          if (kc >= keys_valid) tv = -INFINITY;
+          p[c] = exp2f(tv - m_ref);
+          l_sum += p[c];
+        }
+        // 16 consecutive keys = two 16-byte chunks of this row inside K-block (c0 / 64)
+        const uint32_t rowbase = sP + (c0 >> 6) * 16384 + row * 128;
+        const int ch = (c0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t addr = rowbase + (((ch + q) ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1])), "r"(pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3])),
+                       "r"(pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5])), "r"(pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]))
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    // ---------------- epilogue: O / l -> bf16, LSE ----------------
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l_sum;
+    __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.N + t) * a.ldo + head * 64;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(tO + lane_addr + c0, o);
+      tmem_wait_ld();
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c0 + q * 8) = u;
+        }
+      }
+    }
+    if (valid && a.lse)
+      a.lse[(static_cast<size_t>(b) * a.heads + head) * a.N + t] = m_ref + log2f(l_sum);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace pk
+
+using namespace pk;
+
+// qkv: bf16 [B*N, 3C] (columns (3, head, 64) as produced by the qkv Linear, models_painter.py:76-78)
+// th / tw: bf16 rel-pos tables, zero-padded to th_pad / tw_pad rows (multiples of 16), [rows, 64]
+extern "C" int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void* out, float* lse, int B,
+                           int heads, int h, int w, int th_pad, int tw_pad, void* stream) {
+  PK_CHECK(qkv && th && tw && out, "pk_attn_fwd: null pointer");
+  PK_CHECK(B > 0 && heads > 0 && h > 0 && w > 0, "pk_attn_fwd: bad shape");
+  PK_CHECK(th_pad % 16 == 0 && tw_pad % 16 == 0 && th_pad >= 2 * h - 1 && tw_pad >= 2 * w - 1 &&
+               th_pad <= 256 && tw_pad <= 112,
+           "pk_attn_fwd: bad table padding th_pad=%d tw_pad=%d (h=%d w=%d)", th_pad, tw_pad, h, w);
+  const int N = h * w, C = heads * 64;
+  AttnFwdArgs a;
+  a.h = h;
+  a.N = N;
+  a.heads = heads;
+  a.th_pad = th_pad;
+  a.tw_pad = tw_pad;
+  int relh_bytes = 128 * (h + 1) * 4;
+  if (relh_bytes < 128 * 17 * 4) relh_bytes = 128 * 17 * 4;
+  relh_bytes = (relh_bytes + 15) & ~15;
+  a.relh_bytes = relh_bytes;
+  a.scale_log2 = 0.125f * LOG2E;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.ldo = C;
+  a.lse = lse;
+
+  CUtensorMap tmQ, tmKV, tmTh, tmTw;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(N) * 3 * C * 2};
+    uint32_t boxq[3] = {64, ATT_BM, 1};
+    uint32_t boxk[3] = {64, ATT_KT, 1};
+    if (!make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq)) return 3;
+    if (!make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxk)) return 3;
+    uint64_t d2[2] = {64, static_cast<uint64_t>(th_pad)};
+    uint64_t s2[1] = {128};
+    uint32_t b2[2] = {64, static_cast<uint32_t>(th_pad)};
+    if (!make_tmap_bf16(&tmTh, th, 2, d2, s2, b2)) return 3;
+    d2[1] = tw_pad;
+    b2[1] = tw_pad;
+    if (!make_tmap_bf16(&tmTw, tw, 2, d2, s2, b2)) return 3;
+  }
+  const size_t smem = 1024 + ATT_SRELH + relh_bytes + 128;
+  PK_CHECK(smem <= 227 * 1024, "pk_attn_fwd: h=%d needs %zu B of shared memory", h, smem);
+  dim3 grid((N + ATT_BM - 1) / ATT_BM, heads, B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define PK_ATT_LAUNCH(WW)                                                                                   \
+  case WW: {                                                                                                \
+    static bool attr = false;                                                                               \
+    if (!attr) {                                                                                            \
+      cudaFuncSetAttribute(attn_fwd_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
+      attr = true;                                                                                          \
+    }                                                                                                       \
+    attn_fwd_kernel<WW><<<grid, ATT_THREADS, smem, st>>>(tmQ, tmKV, tmTh, tmTw, a);                         \
+  } break;
+  switch (w) {
+    PK_ATT_LAUNCH(2)
+    PK_ATT_LAUNCH(4)
+    PK_ATT_LAUNCH(7)
+    PK_ATT_LAUNCH(8)
+    PK_ATT_LAUNCH(14)
+    PK_ATT_LAUNCH(28)
+    PK_ATT_LAUNCH(56)
+    default:
+      PK_CHECK(false, "pk_attn_fwd: token-grid width %d unsupported (must divide 112: 2,4,7,8,14,28,56)", w);
+  }
+#undef PK_ATT_LAUNCH
+  PK_LAUNCH_CHECK("pk_attn_fwd");
+  return 0;
+}
+
+// fp32 table [L, 64] -> bf16 [Lpad, 64], rows >= L zero  (rel_pos_h / rel_pos_w, models_painter.py:66-67)
+__global__ void pad_cast_table_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int L,
+                                      int Lpad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Lpad * 64) return;
+  out[idx] = __float2bfloat16_rn(idx < L * 64 ? in[idx] : 0.f);
+}
+extern "C" int pk_relpos_table_bf16(const float* table, void* out_bf16, int L, int Lpad, void* stream) {
+  PK_CHECK(table && out_bf16 && Lpad >= L, "pk_relpos_table_bf16: bad args");
+  pad_cast_table_kernel<<<(Lpad * 64 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      table, static_cast<__nv_bfloat16*>(out_bf16), L, Lpad);
+  PK_LAUNCH_CHECK("pk_relpos_table_bf16");
+  return 0;
+}

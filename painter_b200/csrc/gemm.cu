@@ -14,6 +14,8 @@
 //
 // Reference call sites replaced: every nn.Linear on the path (models_painter.py:60-61,76,87; timm Mlp
 // fc1/fc2 via :201; decoder_embed :327,423) and autograd's mm backward for them.
+#include <string.h>
+
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/painter_b200.h"
@@ -25,14 +27,114 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KiB
 constexpr int GEMM_THREADS = 256;
 
+// internal epilogue kinds (beyond the public PK_EPI_*)
+constexpr int EPI_HEAD = 100;    // decoder head fused behind the 3x3 conv (LN2D + GELU + 1x1 conv + loss)
+constexpr int EPI_UNSHUF = 101;  // inverse pixel shuffle: pixel rows -> token rows [B*h*w, p*p*c]
+
+// Implicit-GEMM modes for the decoder's 3x3 convolution (models_painter.py:328-333):
+//   mode 1: A rows are pixels of an NHWC bf16 image fetched by a 4D TMA box {c, TW, TH, 1}; k-block = tap
+//           (OOB box coordinates give the zero padding).                  used by conv fwd and dgrad
+//   mode 2: wgrad.  out[(tap, c), o] = sum_pix G[pix + tap, c] * dC1[pix, o]; A (MN-major) = G shifted by
+//           the two taps of the m-block, B (MN-major) = dC1; k-blocks run over 64-pixel groups.
+struct ConvArgs {
+  int mode;
+  int H, W, TW, TH, tiles_x, tiles_y;
+};
+struct HeadArgs {
+  const float* tgts;        // [B,3,H,W]
+  const uint8_t* mask;      // [maskB, N]
+  const float* valid;       // [B,3,H,W]
+  __nv_bfloat16* c1_out;    // [B,H,W,64]
+  float* patch_out;         // [B, N, p*p*3]
+  float* num;               // [B] atomics: sum smoothl1 * mask * valid
+  int maskB, p, loss_kind;
+};
+
 struct GemmArgs {
   int M, N, K;
   int BN;
   int stages;
   int transA, transB;
   int num_m_tiles, num_n_tiles;
+  int splits, kb_per_split;  // split-K (epilogue accumulates with fp32 atomics when splits > 1)
   PkEpilogue epi;
+  ConvArgs conv;
+  HeadArgs head;
 };
+
+// decoder-head parameters, refreshed per call by async D2D copies:
+// [0,64) conv bias | [64,128) LN2D gamma | [128,192) LN2D beta | [192,384) 1x1 weight [3][64] | [384,387) 1x1 bias
+__constant__ float c_head[392];
+
+__device__ __forceinline__ float smooth_l1(float d, int kind) {
+  const float ad = fabsf(d);
+  if (kind == 0) return ad < 0.01f ? 0.5f * d * d / 0.01f : ad - 0.005f;  // smoothl1 beta=0.01
+  if (kind == 1) return ad;                                             // l1
+  if (kind == 2) return d * d;                                          // l2
+  return (ad + d * d) * 0.5f;                                           // l1l2
+}
+
+// One pixel (= one accumulator row, 64 conv outputs) of the fused decoder head, models_painter.py:328-333 +
+// vitdet_utils.py:204-209 + forward_loss :433-462 + patchify :355-368.
+__device__ __forceinline__ void head_epilogue_row(const GemmArgs& g, int b, int y, int x, float (&c)[64]) {
+  const HeadArgs& hd = g.head;
+  const int H = g.conv.H, W = g.conv.W, p = hd.p;
+  // conv bias, round to bf16 (the conv output is what backward re-reads), store NHWC
+  float mean = 0.f;
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    c[k] = bf16_round(c[k] + c_head[k]);
+    mean += c[k];
+  }
+  {
+    uint4* d = reinterpret_cast<uint4*>(hd.c1_out + ((static_cast<size_t>(b) * H + y) * W + x) * 64);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 u;
+      u.x = pack_bf16x2(c[q * 8 + 0], c[q * 8 + 1]);
+      u.y = pack_bf16x2(c[q * 8 + 2], c[q * 8 + 3]);
+      u.z = pack_bf16x2(c[q * 8 + 4], c[q * 8 + 5]);
+      u.w = pack_bf16x2(c[q * 8 + 6], c[q * 8 + 7]);
+      d[q] = u;
+    }
+  }
+  mean *= (1.0f / 64);
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    const float dlt = c[k] - mean;
+    var += dlt * dlt;
+  }
+  const float rstd = rsqrtf(var * (1.0f / 64) + 1e-6f);
+  float p0 = c_head[384], p1 = c_head[385], p2 = c_head[386];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    const float ln = c_head[64 + k] * ((c[k] - mean) * rstd) + c_head[128 + k];
+    const float ge = gelu_erf(ln);
+    p0 = fmaf(c_head[192 + k], ge, p0);
+    p1 = fmaf(c_head[256 + k], ge, p1);
+    p2 = fmaf(c_head[320 + k], ge, p2);
+  }
+  const int wt = W / p;
+  const int tok = (y / p) * wt + x / p;
+  const int Ntok = (H / p) * wt;
+  const float m = hd.mask[static_cast<size_t>(b % hd.maskB) * Ntok + tok] ? 1.f : 0.f;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t pix = static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * W + x;
+  const float pr[3] = {p0, p1, p2};
+  float num = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float d = pr[ch] - hd.tgts[pix + ch * plane];
+    num += smooth_l1(d, hd.loss_kind) * (m * hd.valid[pix + ch * plane]);
+  }
+  float* po = hd.patch_out + (static_cast<size_t>(b) * Ntok + tok) * (p * p * 3) + ((y % p) * p + x % p) * 3;
+  po[0] = p0;
+  po[1] = p1;
+  po[2] = p2;
+  num = warp_sum(num);
+  if ((threadIdx.x & 31) == 0) atomicAdd(hd.num + b, num);
+}
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&x)[32]) {
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -72,7 +174,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, int row
     } break;
     case PK_EPI_F32: {
       float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
-      if (e.accumulate) {
+      if (e.accumulate == 2) {  // split-K partials
+        float* df = reinterpret_cast<float*>(d);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(df + j, x[j]);
+      } else if (e.accumulate) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 o = d[q];
@@ -168,7 +274,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
-  const int total_tiles = g.num_m_tiles * g.num_n_tiles;
+  const int tiles_mn = g.num_m_tiles * g.num_n_tiles;
+  const int total_tiles = tiles_mn * g.splits;
   const uint32_t tmem_cols = 2u * BN;
 
   if (warp == 0 && lane == 0) {
@@ -197,23 +304,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ------------------------------ TMA producer ------------------------------
       uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile % g.num_m_tiles, n_blk = tile / g.num_m_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int mn = tile % tiles_mn, split = tile / tiles_mn;
+        const int m_blk = mn % g.num_m_tiles, n_blk = mn / g.num_m_tiles;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), GEMM_A_BYTES + B_BYTES);
           const uint32_t a_dst = sA + s * GEMM_A_BYTES;
           const uint32_t b_dst = sB + s * B_BYTES;
-          if (!g.transA) {
-            tma_load_2d(a_dst, &tmA, full_bar(s), kb * GEMM_BK, m_blk * GEMM_BM);
-          } else {
-            tma_load_2d(a_dst, &tmA, full_bar(s), m_blk * GEMM_BM, kb * GEMM_BK);
-            tma_load_2d(a_dst + 8192, &tmA, full_bar(s), m_blk * GEMM_BM + 64, kb * GEMM_BK);
-          }
-          if (!g.transB) {
+          if (g.conv.mode == 1) {
+            const int tx = m_blk % g.conv.tiles_x, r1 = m_blk / g.conv.tiles_x;
+            const int ty = r1 % g.conv.tiles_y, bi = r1 / g.conv.tiles_y;
+            const int dy = kb / 3, dx = kb - dy * 3;
+            tma_load_4d(a_dst, &tmA, full_bar(s), 0, tx * g.conv.TW + dx - 1, ty * g.conv.TH + dy - 1, bi);
             tma_load_2d(b_dst, &tmB, full_bar(s), kb * GEMM_BK, n_blk * BN);
+          } else if (g.conv.mode == 2) {
+            const int tx = kb % g.conv.tiles_x, r1 = kb / g.conv.tiles_x;
+            const int ty = r1 % g.conv.tiles_y, bi = r1 / g.conv.tiles_y;
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+              const int tap = m_blk * 2 + gi;
+              const int dy = tap / 3, dx = tap - dy * 3;
+              // tap 9 does not exist: a far out-of-bounds box yields the zero rows of the last m-block
+              const int yy = tap < 9 ? ty * g.conv.TH + dy - 1 : -(1 << 20);
+              tma_load_4d(a_dst + gi * 8192, &tmA, full_bar(s), 0, tx * g.conv.TW + dx - 1, yy, bi);
+            }
+            tma_load_4d(b_dst, &tmB, full_bar(s), 0, tx * g.conv.TW, ty * g.conv.TH, bi);
           } else {
-            for (int gi = 0; gi < BN / 64; ++gi)
-              tma_load_2d(b_dst + gi * 8192, &tmB, full_bar(s), n_blk * BN + gi * 64, kb * GEMM_BK);
+            if (!g.transA) {
+              tma_load_2d(a_dst, &tmA, full_bar(s), kb * GEMM_BK, m_blk * GEMM_BM);
+            } else {
+              tma_load_2d(a_dst, &tmA, full_bar(s), m_blk * GEMM_BM, kb * GEMM_BK);
+              tma_load_2d(a_dst + 8192, &tmA, full_bar(s), m_blk * GEMM_BM + 64, kb * GEMM_BK);
+            }
+            if (!g.transB) {
+              tma_load_2d(b_dst, &tmB, full_bar(s), kb * GEMM_BK, n_blk * BN);
+            } else {
+              for (int gi = 0; gi < BN / 64; ++gi)
+                tma_load_2d(b_dst + gi * 8192, &tmB, full_bar(s), n_blk * BN + gi * 64, kb * GEMM_BK);
+            }
           }
           if (++s == static_cast<uint32_t>(stages)) {
             s = 0;
@@ -232,7 +362,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t a_addr = sA + s * GEMM_A_BYTES;
@@ -243,7 +376,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                             : make_sdesc(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = g.transB ? make_sdesc(b_addr + k * 2048, 8192, 1024)
                                             : make_sdesc(b_addr + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
           if (++s == static_cast<uint32_t>(stages)) {
@@ -259,17 +392,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp & 3;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % g.num_m_tiles, n_blk = tile / g.num_m_tiles;
+      const int mn = tile % tiles_mn;
+      const int m_blk = mn % g.num_m_tiles, n_blk = mn / g.num_m_tiles;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + ew * 32 + lane;
+      const int rloc = ew * 32 + lane;
+      const int row = m_blk * GEMM_BM + rloc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c0, v);
-        tmem_wait_ld();
-        if (row < g.M) gemm_epilogue_chunk(g.epi, row, n_blk * BN + c0, v);
+      if (g.conv.mode == 1) {
+        // pixel-row tile: rloc -> (b, y, x)
+        const int tx = m_blk % g.conv.tiles_x, r1 = m_blk / g.conv.tiles_x;
+        const int ty = r1 % g.conv.tiles_y, bi = r1 / g.conv.tiles_y;
+        const int y = ty * g.conv.TH + rloc / g.conv.TW, x = tx * g.conv.TW + rloc % g.conv.TW;
+        if (g.epi.kind == EPI_HEAD) {
+          float c[64];
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(taddr + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c[c0 + j] = __uint_as_float(v[j]);
+          }
+          head_epilogue_row(g, bi, y, x, c);
+        } else {  // EPI_UNSHUF: token row m = (b, y/p, x/p), columns ((y%p)*p + x%p)*64 + c
+          const int p = g.epi.ps_p;
+          const size_t mtok = (static_cast<size_t>(bi) * (g.conv.H / p) + y / p) * (g.conv.W / p) + x / p;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.epi.out) + mtok * g.epi.ldc +
+                               ((y % p) * p + x % p) * 64 + n_blk * BN;
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(taddr + c0, v);
+            tmem_wait_ld();
+            float xv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xv[j] = __uint_as_float(v[j]);
+            store_bf16x32(dst + c0, xv);
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c0, v);
+          tmem_wait_ld();
+          if (row < g.M) gemm_epilogue_chunk(g.epi, row, n_blk * BN + c0, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -284,10 +452,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 int g_force_bn = 0;
+int g_force_splits = 0;
+
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs& g, cudaStream_t st,
+                       const char* who) {
+  const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + g.BN * 128) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    PK_CHECK(e == cudaSuccess, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int total = g.num_m_tiles * g.num_n_tiles * g.splits;
+  const int sms = sm_count();
+  const int grid = total < sms ? total : sms;
+  gemm_bf16_kernel<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g);
+  PK_LAUNCH_CHECK(who);
+  return 0;
+}
+
+static bool conv_tile_geometry(int H, int W, int pixels, int* TW, int* TH) {
+  int tw = W < 64 ? W : 64;
+  if (W % tw != 0 || pixels % tw != 0) return false;
+  int th = pixels / tw;
+  if (H % th != 0) return false;
+  *TW = tw;
+  *TH = th;
+  return true;
+}
+
 }  // namespace pk
 
-// test hook: force the N tile (64/128/256); 0 restores the heuristic
+// test hooks: force the N tile (64/128/256) / the split-K factor; 0 restores the heuristics
 extern "C" void pk_gemm_force_bn(int bn) { pk::g_force_bn = bn; }
+extern "C" void pk_gemm_force_splits(int s) { pk::g_force_splits = s; }
 
 extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, int lda, int ldb,
                             int transA, int transB, const PkEpilogue* epi, void* stream) {
@@ -313,6 +512,7 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
              "pk_gemm_bf16: bad pixel-shuffle geometry");
 
   GemmArgs g;
+  memset(&g, 0, sizeof(g));
   g.M = M;
   g.N = N;
   g.K = K;
@@ -330,6 +530,21 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
   g.stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   g.num_m_tiles = mt;
   g.num_n_tiles = N / BN;
+  // split-K: only for plain fp32 outputs whose tile count cannot fill the machine (wgrad GEMMs);
+  // accumulate == 2 means "out is zero-initialised, add atomically".
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  g.splits = 1;
+  if (epi->kind == PK_EPI_F32 && epi->accumulate == 2) {
+    int want = sms / (g.num_m_tiles * g.num_n_tiles);
+    if (want > 1) {
+      if (want > num_kb / 8) want = num_kb / 8 > 0 ? num_kb / 8 : 1;
+      g.splits = want;
+    }
+    if (g_force_splits > 0) g.splits = g_force_splits < num_kb ? g_force_splits : num_kb;
+  }
+  g.kb_per_split = (num_kb + g.splits - 1) / g.splits;
+  g.splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
+  if (g.splits == 1 && g.epi.kind == PK_EPI_F32 && g.epi.accumulate == 2) g.epi.accumulate = 1;
 
   CUtensorMap tmA, tmB;
   {
@@ -350,17 +565,110 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
     strides[0] = static_cast<uint64_t>(ldb) * 2;
     if (!make_tmap_bf16(&tmB, B, 2, dims, strides, box)) return 3;
   }
-  const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + BN * 128) + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    PK_CHECK(e == cudaSuccess, "pk_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int total = g.num_m_tiles * g.num_n_tiles;
-  const int grid = total < sms ? total : sms;
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, g);
-  PK_LAUNCH_CHECK("pk_gemm_bf16");
-  return 0;
+  return launch_gemm(tmA, tmB, g, static_cast<cudaStream_t>(stream), "pk_gemm_bf16");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder 3x3 convolution (64 -> 64, pad 1) as implicit GEMM over NHWC bf16 (models_painter.py:328-333)
+// ------------------------------------------------------------------------------------------------
+static int conv_common(const void* img_nhwc, const void* wmat, int B, int H, int W, pk::GemmArgs& g,
+                       void* stream, const char* who) {
+  using namespace pk;
+  int TW, TH;
+  PK_CHECK(conv_tile_geometry(H, W, 128, &TW, &TH), "%s: unsupported image size %dx%d", who, H, W);
+  g.M = B * H * W;
+  g.N = 64;
+  g.K = 576;
+  g.BN = 64;
+  g.stages = 8;
+  g.transA = g.transB = 0;
+  g.splits = 1;
+  g.kb_per_split = 9;
+  g.conv.mode = 1;
+  g.conv.H = H; g.conv.W = W; g.conv.TW = TW; g.conv.TH = TH;
+  g.conv.tiles_x = W / TW; g.conv.tiles_y = H / TH;
+  g.num_m_tiles = B * g.conv.tiles_x * g.conv.tiles_y;
+  g.num_n_tiles = 1;
+  CUtensorMap tmA, tmB;
+  uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {128, static_cast<uint64_t>(W) * 128, static_cast<uint64_t>(H) * W * 128};
+  uint32_t box[4] = {64, static_cast<uint32_t>(TW), static_cast<uint32_t>(TH), 1};
+  if (!make_tmap_bf16(&tmA, img_nhwc, 4, dims, strides, box)) return 3;
+  uint64_t d2[2] = {576, 64};
+  uint64_t s2[1] = {576 * 2};
+  uint32_t b2[2] = {64, 64};
+  if (!make_tmap_bf16(&tmB, wmat, 2, d2, s2, b2)) return 3;
+  return launch_gemm(tmA, tmB, g, static_cast<cudaStream_t>(stream), who);
+}
+
+extern "C" int pk_decoder_head_fwd(const void* g_nhwc, const void* wmat, const float* head_params,
+                                   const float* tgts, const uint8_t* mask, int maskB, const float* valid,
+                                   void* c1_out, float* patch_out, float* num, int B, int H, int W, int p,
+                                   int loss_kind, void* stream) {
+  using namespace pk;
+  PK_CHECK(g_nhwc && wmat && head_params && tgts && mask && valid && c1_out && patch_out && num,
+           "pk_decoder_head_fwd: null pointer");
+  PK_CHECK(H % p == 0 && W % p == 0 && maskB >= 1, "pk_decoder_head_fwd: bad geometry");
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_head, head_params, 387 * sizeof(float), 0,
+                                          cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+  PK_CHECK(e == cudaSuccess, "pk_decoder_head_fwd: constant upload: %s", cudaGetErrorString(e));
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.epi.kind = EPI_HEAD;
+  g.epi.alpha = 1.0f;
+  g.head.tgts = tgts; g.head.mask = mask; g.head.valid = valid; g.head.maskB = maskB;
+  g.head.c1_out = static_cast<__nv_bfloat16*>(c1_out);
+  g.head.patch_out = patch_out; g.head.num = num; g.head.p = p; g.head.loss_kind = loss_kind;
+  return conv_common(g_nhwc, wmat, B, H, W, g, stream, "pk_decoder_head_fwd");
+}
+
+// dG (inverse pixel shuffle) [B*h*w, p*p*64] = conv3x3^T(dC1); wmat_t = dgrad weight matrix (flipped taps)
+extern "C" int pk_conv3x3_dgrad_unshuffle(const void* dc1_nhwc, const void* wmat_t, void* out_tok, int B, int H,
+                                          int W, int p, void* stream) {
+  using namespace pk;
+  PK_CHECK(dc1_nhwc && wmat_t && out_tok && H % p == 0 && W % p == 0, "pk_conv3x3_dgrad_unshuffle: bad args");
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.epi.kind = EPI_UNSHUF;
+  g.epi.alpha = 1.0f;
+  g.epi.out = out_tok;
+  g.epi.ldc = p * p * 64;
+  g.epi.ps_p = p;
+  return conv_common(dc1_nhwc, wmat_t, B, H, W, g, stream, "pk_conv3x3_dgrad_unshuffle");
+}
+
+// wgrad: out[(tap*64 + c), o] += sum_pix G[pix + tap, c] * dC1[pix, o]   (out fp32 [576(+pad to 640), 64], zeroed)
+extern "C" int pk_conv3x3_wgrad(const void* g_nhwc, const void* dc1_nhwc, float* out, int B, int H, int W,
+                                void* stream) {
+  using namespace pk;
+  PK_CHECK(g_nhwc && dc1_nhwc && out, "pk_conv3x3_wgrad: null pointer");
+  int TW, TH;
+  PK_CHECK(conv_tile_geometry(H, W, 64, &TW, &TH), "pk_conv3x3_wgrad: unsupported image size %dx%d", H, W);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = 576; g.N = 64; g.K = B * H * W;
+  g.BN = 64; g.stages = 8;
+  g.transA = g.transB = 1;
+  g.conv.mode = 2;
+  g.conv.H = H; g.conv.W = W; g.conv.TW = TW; g.conv.TH = TH;
+  g.conv.tiles_x = W / TW; g.conv.tiles_y = H / TH;
+  g.num_m_tiles = 5; g.num_n_tiles = 1;
+  const int num_kb = B * g.conv.tiles_x * g.conv.tiles_y;
+  int splits = sm_count() / 5;
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  g.kb_per_split = (num_kb + splits - 1) / splits;
+  g.splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
+  g.epi.kind = PK_EPI_F32;
+  g.epi.out = out;
+  g.epi.ldc = 64;
+  g.epi.alpha = 1.0f;
+  g.epi.accumulate = 2;
+  CUtensorMap tmA, tmB;
+  uint64_t dims[4] = {64, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {128, static_cast<uint64_t>(W) * 128, static_cast<uint64_t>(H) * W * 128};
+  uint32_t box[4] = {64, static_cast<uint32_t>(TW), static_cast<uint32_t>(TH), 1};
+  if (!make_tmap_bf16(&tmA, g_nhwc, 4, dims, strides, box)) return 3;
+  if (!make_tmap_bf16(&tmB, dc1_nhwc, 4, dims, strides, box)) return 3;
+  return launch_gemm(tmA, tmB, g, static_cast<cudaStream_t>(stream), "pk_conv3x3_wgrad");
 }

@@ -88,3 +88,31 @@ def gemm(a, b, *, trans_a=False, trans_b=False, kind=EPI_BF16, out=None, out2=No
     if kind == EPI_GELU:
         return out, out2
     return out
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def relpos_table_bf16(table):
+    """fp32 [L, 64] rel-pos table -> zero-padded bf16 [pad16(L), 64] (attention kernel operand)."""
+    _req(table, torch.float32, "table")
+    assert table.dim() == 2 and table.shape[1] == 64 and table.is_contiguous()
+    L = table.shape[0]
+    out = torch.empty((_pad16(L), 64), dtype=torch.bfloat16, device=table.device)
+    check(lib().pk_relpos_table_bf16(_ptr(table), _ptr(out), L, out.shape[0], _stream()), "pk_relpos_table_bf16")
+    return out
+
+
+def attn_fwd(qkv, th, tw, B, heads, h, w, need_lse=True):
+    """Fused attention forward. qkv: bf16 [B*h*w, 3*heads*64]; th/tw: padded bf16 tables for an (h, w) grid.
+    Returns (out bf16 [B*h*w, heads*64], lse fp32 [B*heads, h*w] in the log2 domain)."""
+    _req(qkv, torch.bfloat16, "qkv")
+    N, C = h * w, heads * 64
+    assert qkv.is_contiguous() and tuple(qkv.shape) == (B * N, 3 * C)
+    assert th.shape[0] >= 2 * h - 1 and tw.shape[0] >= 2 * w - 1
+    out = torch.empty((B * N, C), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B * heads, N), dtype=torch.float32, device=qkv.device) if need_lse else None
+    check(lib().pk_attn_fwd(_ptr(qkv), _ptr(th), _ptr(tw), _ptr(out), _ptr(lse), B, heads, h, w,
+                            th.shape[0], tw.shape[0], _stream()), "pk_attn_fwd")
+    return out, lse

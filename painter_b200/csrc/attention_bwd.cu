@@ -1,0 +1,711 @@
+// painter_b200 — fused attention backward with decomposed relative-position bias (sm_100a, tcgen05).
+//
+// Two kernels, both recomputing S = Q.K^T (+bias) tile by tile like the forward (attention_fwd.cu):
+//
+//  A) attn_bwd_dq_kernel   CTA = 128 query rows, loops over key tiles (112 keys = R image rows).
+//       dP = dO.V^T, P = exp2(t - LSE), dS = P * (dP - delta)
+//       dQ   = 0.125 * dS.K  +  Gh^.T_h  +  Gw^.T_w          (all on tensor cores)
+//       dT_h = Gh^^T.Q , dT_w = Gw^^T.Q                       (tensor cores, then fp32 atomics)
+//     where Gh'[r,i] = sum_{u in image row i} dS[r,u], Gw'[r,j] = sum_{u in image col j} dS[r,u] and
+//     Gh^[r,t] = Gh'[r, i_r + h-1 - t] is the Toeplitz re-indexing matching the table row t.
+//     Also emits rel_h / rel_w (log2e-scaled bias rows) and delta = rowsum(dO * O) for kernel B.
+//
+//  B) attn_bwd_dkv_kernel  CTA = one key tile, loops over query tiles.
+//       dV = P^T.dO , dK = 0.125 * dS^T.Q     (P / dS tiles in smem are read as MN-major A operands)
+//
+// Reference math: autograd of models_painter.py:80-86 + vitdet_utils.py:113-123.
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/painter_b200.h"
+
+namespace pk {
+
+constexpr int AB_BM = 128;
+constexpr int AB_KT = 112;
+constexpr int AB_THREADS = 192;
+constexpr float AB_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ================================================================================================
+// Kernel A
+// ================================================================================================
+// smem map (offsets from the 1024-aligned base)
+constexpr uint32_t A_SQ = 0;                    // Q tile 128 x 128 B
+constexpr uint32_t A_SDO = 16384;               // dO tile
+constexpr uint32_t A_SDS = 32768;               // dS tile (2 K-blocks); T_h staged here in the prologue;
+                                                // epilogue: G^ buffer (up to 4 K-blocks = 64 KiB from here)
+constexpr uint32_t A_SKV = A_SDS + 32768;       // 2 stages x (K 14336 | V 14336)
+constexpr uint32_t A_STH = A_SDS + 65536;       // epilogue: T_h reload (<= 28 KiB), after the 64 KiB G^ buffer
+constexpr uint32_t A_STW = A_STH + 28672;       // epilogue: T_w reload (<= 14 KiB)
+constexpr uint32_t A_SRELH = A_STW + 14336;     // rel_h rows fp32 [128][h+1]; Gh' sums overwrite them in place
+static_assert(A_SKV + 57344 <= A_SRELH, "K/V stages must end before the rel_h region");
+
+struct AttnBwdArgs {
+  int h, N, heads;
+  int th_pad, tw_pad;
+  int relh_bytes;   // size of the rel_h / Gh' region
+  float scale_log2;
+  const __nv_bfloat16* O;    // [B*N, C]
+  const __nv_bfloat16* dO;   // [B*N, C]
+  const float* lse;          // [B*heads, N]
+  float* delta;              // [B*heads, N]
+  float* relh_g;             // [B*heads, N, h]   (log2e-scaled)
+  float* relw_g;             // [B*heads, N, W]
+  __nv_bfloat16* dqkv;       // [B*N, 3C]
+  float* dTh;                // [2h-1, 64] fp32 atomics
+  float* dTw;                // [2W-1, 64]
+};
+
+template <int W>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmTh,
+                   const __grid_constant__ CUtensorMap tmTw, const AttnBwdArgs a) {
+  constexpr int R = AB_KT / W;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_base = smem_u32(smem_raw);
+  const uint32_t base = (raw_base + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_base);
+
+  const uint32_t sQ = base + A_SQ, sdO = base + A_SDO, sdS = base + A_SDS, sKV = base + A_SKV;
+  const uint32_t sTh = base + A_STH, sTw = base + A_STW;
+  float* relh_gen = reinterpret_cast<float*>(gen + A_SRELH);
+  const uint32_t bar0 = base + A_SRELH + a.relh_bytes;
+  const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*2*/, bar_ke = bar0 + 24 /*2*/, bar_s = bar0 + 40,
+                 bar_p = bar0 + 48, bar_g = bar0 + 56, bar_gr = bar0 + 64, bar_e = bar0 + 72,
+                 bar_er = bar0 + 80, bar_t = bar0 + 88;
+  const uint32_t holder = bar0 + 96;
+  volatile uint32_t* holder_gen =
+      reinterpret_cast<volatile uint32_t*>(gen + A_SRELH + a.relh_bytes + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AB_BM;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int C = a.heads * 64;
+  const int h = a.h;
+  const int num_tiles = (h + R - 1) / R;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmdO);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kf, 1);
+    mbar_init(bar_kf + 8, 1);
+    mbar_init(bar_ke, 1);
+    mbar_init(bar_ke + 8, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_g, 1);
+    mbar_init(bar_gr, 128);
+    mbar_init(bar_e, 1);
+    mbar_init(bar_er, 128);
+    mbar_init(bar_t, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *holder_gen;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      mbar_expect_tx(bar_q, 32768u + static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u);
+      tma_load_3d(sQ, &tmQ, bar_q, head * 64, q0, b);
+      tma_load_3d(sdO, &tmdO, bar_q, head * 64, q0, b);
+      tma_load_2d(sdS, &tmTh, bar_q, 0, 0);                 // T_h: th_pad <= 224 rows -> 28 KiB <= 32 KiB
+      tma_load_2d(sKV + 28672 + 14336, &tmTw, bar_q, 0, 0);  // T_w in the stage-1 V buffer
+      for (int j = 0; j < num_tiles; ++j) {
+        const int st = j & 1;
+        if (j >= 2) mbar_wait(bar_ke + 8 * st, ((j >> 1) - 1) & 1);
+        if (j == 1) mbar_wait(bar_g, 0);  // G_w MMA done with T_w (stage-1 V buffer)
+        mbar_expect_tx(bar_kf + 8 * st, 2 * AB_KT * 128);
+        tma_load_3d(sKV + st * 28672, &tmKV, bar_kf + 8 * st, C + head * 64, j * AB_KT, b);
+        tma_load_3d(sKV + st * 28672 + 14336, &tmKV, bar_kf + 8 * st, 2 * C + head * 64, j * AB_KT, b);
+      }
+      // epilogue: reload the tables as MN-major B operands once every main-loop MMA has retired
+      mbar_wait(bar_e, 0);
+      mbar_expect_tx(bar_t, static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u);
+      tma_load_2d(sTh, &tmTh, bar_t, 0, 0);
+      tma_load_2d(sTw, &tmTw, bar_t, 0, 0);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // -------------------------------------- MMA issuer --------------------------------------
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      {  // G_w = Q . T_w^T
+        const uint32_t idesc = make_idesc_bf16(128, a.tw_pad, false, false);
+        const uint32_t sT = sKV + 28672 + 14336;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sT + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(bar_g);
+      }
+      mbar_wait(bar_gr, 0);
+      tc_fence_after();
+      {  // G_h = Q . T_h^T
+        const uint32_t idesc = make_idesc_bf16(128, a.th_pad, false, false);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sdS + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(bar_g);
+      }
+      mbar_wait(bar_gr, 1);
+      tc_fence_after();
+      const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
+      const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
+      for (int j = 0; j < num_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t sK = sKV + st * 28672, sV = sK + 14336;
+        mbar_wait(bar_kf + 8 * st, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sK + k * 32, 16, 1024), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tdP, make_sdesc(sdO + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc_s, k != 0);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < AB_KT / 16; ++kk)
+          umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                  make_sdesc(sK + kk * 2048, 16, 1024), idesc_dq, (j | kk) != 0);
+        umma_commit(bar_ke + 8 * st);
+      }
+      umma_commit(bar_e);  // completion #1 (parity 0): main loop retired
+      // ---- epilogue phase 1: dQ += Gh^ . T_h ; dT_h = Gh^^T . Q ----
+      const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
+      mbar_wait(bar_er, 0);
+      mbar_wait(bar_t, 0);
+      tc_fence_after();
+      for (int kk = 0; kk < a.th_pad / 16; ++kk)
+        umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                make_sdesc(sTh + kk * 2048, 16, 1024), idesc_dq, 1u);
+      for (int mh = 0; mh * 128 < a.th_pad; ++mh)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tS + mh * 64, make_sdesc(sdS + (2 * mh) * 16384 + kk * 2048, 16384, 1024),
+                  make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt, kk != 0);
+      umma_commit(bar_e);  // completion #2 (parity 1)
+      // ---- epilogue phase 2: dQ += Gw^ . T_w ; dT_w = Gw^^T . Q ----
+      mbar_wait(bar_er, 1);
+      tc_fence_after();
+      for (int kk = 0; kk < a.tw_pad / 16; ++kk)
+        umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                make_sdesc(sTw + kk * 2048, 16, 1024), idesc_dq, 1u);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        umma_ss(tS, make_sdesc(sdS + kk * 2048, 16384, 1024), make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt,
+                kk != 0);
+      umma_commit(bar_e);  // completion #3 (parity 0)
+    }
+  } else {
+    // ------------------------------------ softmax warps ------------------------------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    int t = q0 + row;
+    const bool valid = t < a.N;
+    if (!valid) t = a.N - 1;
+    const int i_r = t / W, j_r = t - i_r * W;
+    const int ldr = h + 1;
+    float* my_relh = relh_gen + static_cast<size_t>(row) * ldr;
+    float* my_gh = my_relh;  // rel_h[i] is consumed (tile i / R) before Gh'[i] is produced: same storage
+    const size_t bh = static_cast<size_t>(b) * a.heads + head;
+
+    // delta = rowsum(dO * O), LSE
+    float delta = 0.f;
+    {
+      const uint4* po = reinterpret_cast<const uint4*>(a.O + (static_cast<size_t>(b) * a.N + t) * C + head * 64);
+      const uint4* pd = reinterpret_cast<const uint4*>(a.dO + (static_cast<size_t>(b) * a.N + t) * C + head * 64);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 o = po[q], d = pd[q];
+        const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          delta += __uint_as_float(ow[e] << 16) * __uint_as_float(dw[e] << 16);
+          delta += __uint_as_float(ow[e] & 0xFFFF0000u) * __uint_as_float(dw[e] & 0xFFFF0000u);
+        }
+      }
+    }
+    const float lse = a.lse[bh * a.N + t];
+    if (valid) a.delta[bh * a.N + t] = delta;
+
+    // ---- rel_w -> registers (+ global for kernel B) ----
+    float relw[W];
+    {
+      float* scratch = relh_gen + static_cast<size_t>(row) * 17;
+      mbar_wait(bar_g, 0);
+      tc_fence_after();
+      for (int c0 = 0; c0 < a.tw_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) scratch[c] = __uint_as_float(v[c]) * AB_LOG2E;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const int tt = j_r + (W - 1) - j - c0;
+          if (tt >= 0 && tt < 16) relw[j] = scratch[tt];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive(bar_gr);
+      if (valid) {
+        float* dst = a.relw_g + (bh * a.N + t) * W;
+#pragma unroll
+        for (int j = 0; j < W; ++j) dst[j] = relw[j];
+      }
+    }
+    // ---- rel_h -> smem (+ global) ; zero the Gh' row ----
+    {
+      mbar_wait(bar_g, 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < a.th_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int i = i_r + (h - 1) - (c0 + c);
+          if (i >= 0 && i < h) my_relh[i] = __uint_as_float(v[c]) * AB_LOG2E;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive(bar_gr);
+      if (valid) {
+        float* dst = a.relh_g + (bh * a.N + t) * h;
+        for (int i = 0; i < h; ++i) dst[i] = my_relh[i];
+      }
+    }
+
+    float gw[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) gw[j] = 0.f;
+    const float sc = a.scale_log2;
+    for (int j = 0; j < num_tiles; ++j) {
+      float hb[R], gh[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = j * R + r;
+        hb[r] = my_relh[i < h ? i : h - 1];
+        gh[r] = 0.f;
+      }
+      const int keys_valid = (h - j * R) * W;
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < AB_KT; c0 += 16) {
+        uint32_t v[16], w[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_ld_x16(tdP + lane_addr + c0, w);
+        tmem_wait_ld();
+        float ds[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int kc = c0 + c;
+          const float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
+          float p = exp2f(tv - lse);
+          if (kc >= keys_valid || !valid) p = 0.f;
+          ds[c] = p * (__uint_as_float(w[c]) - delta);
+          gh[kc / W] += ds[c];
+          gw[kc % W] += ds[c];
+          ds[c] *= 0.125f;
+        }
+        const uint32_t rowbase = sdS + (c0 >> 6) * 16384 + row * 128;
+        const int ch = (c0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          st_shared_v4(rowbase + (((ch + q) ^ (row & 7)) << 4), pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
+                       pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]), pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]),
+                       pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = j * R + r;
+        if (i < h) my_gh[i] = gh[r];
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+
+    // ---------------- epilogue phase 1: Gh^ (bf16, K-major / MN-major dual view) ----------------
+    mbar_wait(bar_e, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < a.th_pad; c0 += 8) {
+      float g[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int i = i_r + (h - 1) - (c0 + c);
+        g[c] = (i >= 0 && i < h) ? my_gh[i] : 0.f;
+      }
+      const uint32_t addr = sdS + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+      st_shared_v4(addr, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                   pack_bf16x2(g[6], g[7]));
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_er);
+    // ---------------- epilogue phase 2: dT_h atomics, then Gw^ ----------------
+    mbar_wait(bar_e, 1);
+    tc_fence_after();
+    for (int mh = 0; mh * 128 < a.th_pad; ++mh) {
+      const int tt = mh * 128 + row;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + mh * 64 + c0, v);
+        tmem_wait_ld();
+        if (tt < 2 * h - 1) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) atomicAdd(a.dTh + tt * 64 + c0 + c, __uint_as_float(v[c]));
+        }
+      }
+    }
+    {
+      // zero this row of the first two K-blocks, then scatter gw[j] to column t = j_r + W-1 - j
+      const uint32_t rb0 = sdS + row * 128, rb1 = sdS + 16384 + row * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        st_shared_v4(rb0 + (q << 4), 0u, 0u, 0u, 0u);
+        st_shared_v4(rb1 + (q << 4), 0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const int tt = j_r + (W - 1) - j;
+        const uint32_t addr = sdS + (tt >> 6) * 16384 + row * 128 + ((((tt & 63) >> 3) ^ (row & 7)) << 4) +
+                              (tt & 7) * 2;
+        const __nv_bfloat16 bv = __float2bfloat16_rn(gw[j]);
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&bv)) : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_er);
+    // ---------------- epilogue phase 3: dT_w atomics, dQ -> bf16 ----------------
+    mbar_wait(bar_e, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tS + lane_addr + c0, v);
+      tmem_wait_ld();
+      if (row < 2 * W - 1) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) atomicAdd(a.dTw + row * 64 + c0 + c, __uint_as_float(v[c]));
+      }
+    }
+    __nv_bfloat16* qrow = a.dqkv + (static_cast<size_t>(b) * a.N + t) * (3 * C) + head * 64;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(tdQ + lane_addr + c0, o);
+      tmem_wait_ld();
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]), __uint_as_float(o[q * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7]));
+          *reinterpret_cast<uint4*>(qrow + c0 + q * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ================================================================================================
+// Kernel B
+// ================================================================================================
+constexpr uint32_t B_SK = 0;                 // K tile 112 x 128 B
+constexpr uint32_t B_SV = 14336;             // V tile
+constexpr uint32_t B_SQ = 28672;             // 2 stages x (Q 16384 | dO 16384)
+constexpr uint32_t B_SP = B_SQ + 65536;      // P tile  (2 K-blocks)
+constexpr uint32_t B_SDS = B_SP + 32768;     // dS tile (2 K-blocks)
+constexpr uint32_t B_BARS = B_SDS + 32768;
+
+template <int W>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmdO, const AttnBwdArgs a) {
+  constexpr int R = AB_KT / W;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_base = smem_u32(smem_raw);
+  const uint32_t base = (raw_base + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_base);
+  const uint32_t sK = base + B_SK, sV = base + B_SV, sQ0 = base + B_SQ, sP = base + B_SP, sdS = base + B_SDS;
+  const uint32_t bar0 = base + B_BARS;
+  const uint32_t bar_kv = bar0, bar_qf = bar0 + 8 /*2*/, bar_qe = bar0 + 24 /*2*/, bar_s = bar0 + 40,
+                 bar_p = bar0 + 48, bar_o = bar0 + 56;
+  const uint32_t holder = bar0 + 64;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B_BARS + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x;  // key tile
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int C = a.heads * 64;
+  const int h = a.h;
+  const int num_q = (a.N + AB_BM - 1) / AB_BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmdO);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_qf, 1);
+    mbar_init(bar_qf + 8, 1);
+    mbar_init(bar_qe, 1);
+    mbar_init(bar_qe + 8, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *holder_gen;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_kv, 2 * AB_KT * 128);
+      tma_load_3d(sK, &tmKV, bar_kv, C + head * 64, jt * AB_KT, b);
+      tma_load_3d(sV, &tmKV, bar_kv, 2 * C + head * 64, jt * AB_KT, b);
+      for (int i = 0; i < num_q; ++i) {
+        const int st = i & 1;
+        if (i >= 2) mbar_wait(bar_qe + 8 * st, ((i >> 1) - 1) & 1);
+        mbar_expect_tx(bar_qf + 8 * st, 32768);
+        tma_load_3d(sQ0 + st * 32768, &tmQ, bar_qf + 8 * st, head * 64, i * AB_BM, b);
+        tma_load_3d(sQ0 + st * 32768 + 16384, &tmdO, bar_qf + 8 * st, head * 64, i * AB_BM, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
+      const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
+      mbar_wait(bar_kv, 0);
+      for (int i = 0; i < num_q; ++i) {
+        const int st = i & 1;
+        const uint32_t sQ = sQ0 + st * 32768, sdO = sQ + 16384;
+        mbar_wait(bar_qf + 8 * st, (i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sK + k * 32, 16, 1024), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tdP, make_sdesc(sdO + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc_s, k != 0);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, i & 1);
+        tc_fence_after();
+        // dV[keys, d] += P^T . dO ;  dK[keys, d] += dS^T . Q   (A: MN-major view of the [q rows][keys] tiles)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tdV, make_sdesc(sP + kk * 2048, 16384, 1024), make_sdesc(sdO + kk * 2048, 16, 1024), idesc_tt,
+                  (i | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tdK, make_sdesc(sdS + kk * 2048, 16384, 1024), make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt,
+                  (i | kk) != 0);
+        umma_commit(bar_qe + 8 * st);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const size_t bh = static_cast<size_t>(b) * a.heads + head;
+    const float sc = a.scale_log2;
+    const int keys_valid = (h - jt * R) * W;
+    for (int i = 0; i < num_q; ++i) {
+      int t = i * AB_BM + row;
+      const bool valid = t < a.N;
+      if (!valid) t = a.N - 1;
+      const float lse = a.lse[bh * a.N + t];
+      const float delta = a.delta[bh * a.N + t];
+      float hb[R], relw[W];
+      {
+        const float* ph = a.relh_g + (bh * a.N + t) * h;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int ii = jt * R + r;
+          hb[r] = ph[ii < h ? ii : h - 1];
+        }
+        const float* pw = a.relw_g + (bh * a.N + t) * W;
+#pragma unroll
+        for (int j = 0; j < W; ++j) relw[j] = pw[j];
+      }
+      mbar_wait(bar_s, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < AB_KT; c0 += 16) {
+        uint32_t v[16], w[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_ld_x16(tdP + lane_addr + c0, w);
+        tmem_wait_ld();
+        float p[16], ds[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int kc = c0 + c;
+          const float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
+          p[c] = exp2f(tv - lse);
+          if (kc >= keys_valid || !valid) p[c] = 0.f;
+          ds[c] = p[c] * (__uint_as_float(w[c]) - delta) * 0.125f;
+        }
+        const uint32_t off = (c0 >> 6) * 16384 + row * 128;
+        const int ch = (c0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t sw = (((ch + q) ^ (row & 7)) << 4);
+          st_shared_v4(sP + off + sw, pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]), pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]),
+                       pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5]), pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]));
+          st_shared_v4(sdS + off + sw, pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
+                       pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]), pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]),
+                       pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    // epilogue: accumulator row = key (jt*112 + row), rows >= 112 are padding
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const int u = jt * AB_KT + row;
+    const bool kvalid = row < AB_KT && u < a.N;
+    __nv_bfloat16* krow = a.dqkv + (static_cast<size_t>(b) * a.N + (kvalid ? u : 0)) * (3 * C) + C + head * 64;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tacc = which == 0 ? tdK : tdV;
+      __nv_bfloat16* dst = krow + which * C;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld_x16(tacc + lane_addr + c0, o);
+        tmem_wait_ld();
+        if (kvalid) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint4 uu;
+            uu.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]), __uint_as_float(o[q * 8 + 1]));
+            uu.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3]));
+            uu.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5]));
+            uu.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c0 + q * 8) = uu;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace pk
+
+using namespace pk;
+
+// qkv / dqkv: bf16 [B*N, 3C];  O, dO: bf16 [B*N, C];  lse: fp32 [B*heads, N] from pk_attn_fwd
+// scratch buffers (caller-allocated): delta [B*heads*N], relh_g [B*heads*N*h], relw_g [B*heads*N*w] fp32
+// dTh [2h-1, 64], dTw [2w-1, 64]: fp32, accumulated atomically (caller zero-initialises)
+extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
+                           const void* tw, void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g,
+                           float* relw_g, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream) {
+  PK_CHECK(qkv && O && dO && lse && th && tw && dqkv && dTh && dTw && delta && relh_g && relw_g,
+           "pk_attn_bwd: null pointer");
+  PK_CHECK(th_pad % 16 == 0 && tw_pad % 16 == 0 && th_pad >= 2 * h - 1 && tw_pad >= 2 * w - 1 &&
+               th_pad <= 224 && tw_pad <= 112,
+           "pk_attn_bwd: bad table padding th_pad=%d tw_pad=%d (h=%d w=%d)", th_pad, tw_pad, h, w);
+  const int N = h * w, C = heads * 64;
+  AttnBwdArgs a;
+  a.h = h; a.N = N; a.heads = heads; a.th_pad = th_pad; a.tw_pad = tw_pad;
+  int relh_bytes = 128 * (h + 1) * 4;
+  if (relh_bytes < 20480) relh_bytes = 20480;
+  relh_bytes = (relh_bytes + 15) & ~15;
+  a.relh_bytes = relh_bytes;
+  a.scale_log2 = 0.125f * AB_LOG2E;
+  a.O = static_cast<const __nv_bfloat16*>(O);
+  a.dO = static_cast<const __nv_bfloat16*>(dO);
+  a.lse = lse; a.delta = delta; a.relh_g = relh_g; a.relw_g = relw_g;
+  a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  a.dTh = dTh; a.dTw = dTw;
+
+  CUtensorMap tmQ, tmKV, tmdO, tmTh, tmTw;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(N) * 3 * C * 2};
+    uint32_t boxq[3] = {64, AB_BM, 1};
+    uint32_t boxk[3] = {64, AB_KT, 1};
+    if (!make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq)) return 3;
+    if (!make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxk)) return 3;
+    uint64_t dimo[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+    uint64_t strideo[2] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(N) * C * 2};
+    if (!make_tmap_bf16(&tmdO, dO, 3, dimo, strideo, boxq)) return 3;
+    uint64_t d2[2] = {64, static_cast<uint64_t>(th_pad)};
+    uint64_t s2[1] = {128};
+    uint32_t b2[2] = {64, static_cast<uint32_t>(th_pad)};
+    if (!make_tmap_bf16(&tmTh, th, 2, d2, s2, b2)) return 3;
+    d2[1] = tw_pad;
+    b2[1] = tw_pad;
+    if (!make_tmap_bf16(&tmTw, tw, 2, d2, s2, b2)) return 3;
+  }
+  const size_t smemA = 1024 + A_SRELH + static_cast<size_t>(relh_bytes) + 128;
+  const size_t smemB = 1024 + B_BARS + 128;
+  PK_CHECK(smemA <= 227 * 1024, "pk_attn_bwd: h=%d needs %zu B of shared memory", h, smemA);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 gridA((N + AB_BM - 1) / AB_BM, heads, B);
+  const int R = AB_KT / w;
+  dim3 gridB((h + R - 1) / R, heads, B);
+#define PK_ATTB_LAUNCH(WW)                                                                                     \
+  case WW: {                                                                                                   \
+    static bool attr = false;                                                                                  \
+    if (!attr) {                                                                                               \
+      cudaFuncSetAttribute(attn_bwd_dq_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
+      cudaFuncSetAttribute(attn_bwd_dkv_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  \
+      attr = true;                                                                                             \
+    }                                                                                                          \
+    attn_bwd_dq_kernel<WW><<<gridA, AB_THREADS, smemA, st>>>(tmQ, tmKV, tmdO, tmTh, tmTw, a);                  \
+    PK_LAUNCH_CHECK("pk_attn_bwd(dq)");                                                                        \
+    attn_bwd_dkv_kernel<WW><<<gridB, AB_THREADS, smemB, st>>>(tmQ, tmKV, tmdO, a);                             \
+    PK_LAUNCH_CHECK("pk_attn_bwd(dkv)");                                                                       \
+  } break;
+  switch (w) {
+    PK_ATTB_LAUNCH(2)
+    PK_ATTB_LAUNCH(4)
+    PK_ATTB_LAUNCH(7)
+    PK_ATTB_LAUNCH(8)
+    PK_ATTB_LAUNCH(14)
+    PK_ATTB_LAUNCH(28)
+    PK_ATTB_LAUNCH(56)
+    default:
+      PK_CHECK(false, "pk_attn_bwd: token-grid width %d unsupported (must divide 112)", w);
+  }
+#undef PK_ATTB_LAUNCH
+  return 0;
+}

@@ -1,0 +1,236 @@
+// painter_b200 — decoder-side helper kernels: conv weight packing, loss bookkeeping and the backward of
+// the fused head (LayerNorm2D + GELU + 1x1 conv + masked smooth-L1).  The 3x3 convolution itself runs as
+// an implicit GEMM on tcgen05 (gemm.cu, conv modes).
+//
+// Reference: Painter/models_painter.py:328-333 (decoder_pred), util/vitdet_utils.py:189-209 (LayerNorm2D),
+// models_painter.py:433-462 (forward_loss), SegGPT variant models_seggpt.py:448-469.
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/painter_b200.h"
+
+namespace pk {
+
+// ---------------------------------------------------------------------------------------------
+// Conv weight [O=64, C=64, 3, 3] fp32  ->  bf16 GEMM operands
+//   fwd  : Wf[o, tap*64 + c]  = W[o, c, dy, dx]            tap = dy*3 + dx
+//   dgrad: Wd[c, tap*64 + o]  = W[o, c, 2-dy, 2-dx]
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                 __nv_bfloat16* __restrict__ wd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 576) return;
+  const int o = idx / 576, k = idx % 576, tap = k / 64, c = k % 64;
+  const int dy = tap / 3, dx = tap % 3;
+  wf[idx] = __float2bfloat16_rn(w[((o * 64 + c) * 3 + dy) * 3 + dx]);
+  // here (o, c) play (row = input channel c', column channel o'): row index "o" is the dgrad output channel
+  wd[idx] = __float2bfloat16_rn(w[((c * 64 + o) * 3 + (2 - dy)) * 3 + (2 - dx)]);
+}
+
+// wgrad GEMM result acc[(tap*64 + c), o]  ->  dW[o, c, dy, dx]
+__global__ void conv_wgrad_unpack_kernel(const float* __restrict__ acc, float* __restrict__ dw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64 * 9) return;
+  const int o = idx / 576, r = idx % 576, c = r / 9, tap = r % 9;
+  dw[idx] = acc[(tap * 64 + c) * 64 + o];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Loss bookkeeping (forward_loss): per-sample
+//   stats[b][0] = sum_{c,y,x} (tgt*std_c + mean_c) * (1 - M)      ("is the unmasked target black?")
+//   stats[b][1] = sum_{c,y,x} M * valid
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+loss_prep_kernel(const float* __restrict__ tgts, const uint8_t* __restrict__ mask, int maskB,
+                 const float* __restrict__ valid, float* __restrict__ stats, int H, int W, int p) {
+  const int b = blockIdx.y;
+  const int wt = W / p, Ntok = (H / p) * wt;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  float s0 = 0.f, s1 = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < plane;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int y = static_cast<int>(i / W), x = static_cast<int>(i % W);
+    const float m = mask[static_cast<size_t>(b % maskB) * Ntok + (y / p) * wt + x / p] ? 1.f : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t o = (static_cast<size_t>(b) * 3 + c) * plane + i;
+      s0 += (tgts[o] * stdv[c] + mean[c]) * (1.f - m);
+      s1 += m * valid[o];
+    }
+  }
+  __shared__ float r0[8], r1[8];
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) {
+    r0[threadIdx.x >> 5] = s0;
+    r1[threadIdx.x >> 5] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      a += r0[w];
+      c += r1[w];
+    }
+    atomicAdd(stats + 2 * b, a);
+    atomicAdd(stats + 2 * b + 1, c);
+  }
+}
+
+// loss = sum_b keep_b num_b / (sum_b keep_b den_b + eps);  coef[b] = keep_b / (that denominator)
+__global__ void loss_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ num,
+                                     float* __restrict__ loss, float* __restrict__ coef, int B, int seggpt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float n = 0.f, d = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float keep = (seggpt || !(stats[2 * b] < 300.f)) ? 1.f : 0.f;
+    n += keep * num[b];
+    d += keep * stats[2 * b + 1];
+  }
+  const float den = seggpt ? d : d + 1e-2f;
+  loss[0] = n / den;
+  for (int b = 0; b < B; ++b) {
+    const float keep = (seggpt || !(stats[2 * b] < 300.f)) ? 1.f : 0.f;
+    coef[b] = keep / den;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the fused head, one warp per pixel (lane owns channels 2*lane, 2*lane+1).
+//   recompute: xh = (c1 - mu) rstd; ln = g*xh + b; ge = gelu(ln); pred = W1 ge + b1
+//   dpred_c = gscale * coef[b] * M * valid_c * dloss/dpred;   back through 1x1, GELU, LN2D -> dC1 (bf16)
+//   param grads accumulate in registers, one atomic per lane per block at the end.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const __nv_bfloat16* __restrict__ c1, const float* __restrict__ tgts,
+                const uint8_t* __restrict__ mask, int maskB, const float* __restrict__ valid,
+                const float* __restrict__ coef, const float* __restrict__ gscale,
+                const float* __restrict__ hp /* head params, 387 floats */, __nv_bfloat16* __restrict__ dc1,
+                float* __restrict__ dhp /* grads of [gamma 64 | beta 64 | w 192 | b 3] at offsets 64.. */,
+                int B, int H, int W, int p, int loss_kind) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int k0 = 2 * lane, k1 = 2 * lane + 1;
+  const float ga0 = hp[64 + k0], ga1 = hp[64 + k1], be0 = hp[128 + k0], be1 = hp[128 + k1];
+  float w0[3], w1[3], b1[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    w0[c] = hp[192 + c * 64 + k0];
+    w1[c] = hp[192 + c * 64 + k1];
+    b1[c] = hp[384 + c];
+  }
+  const float gs = gscale ? gscale[0] : 1.f;
+  const int wt = W / p, Ntok = (H / p) * wt;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t npix = static_cast<size_t>(B) * plane;
+  float dga0 = 0, dga1 = 0, dbe0 = 0, dbe1 = 0, dw0[3] = {0, 0, 0}, dw1[3] = {0, 0, 0}, db1[3] = {0, 0, 0};
+  for (size_t pix = gw; pix < npix; pix += warps_total) {
+    const int b = static_cast<int>(pix / plane);
+    const size_t yx = pix % plane;
+    const int y = static_cast<int>(yx / W), x = static_cast<int>(yx % W);
+    const uint32_t u = reinterpret_cast<const uint32_t*>(c1)[pix * 32 + lane];
+    const float x0 = __uint_as_float(u << 16), x1 = __uint_as_float(u & 0xFFFF0000u);
+    const float mean = warp_sum(x0 + x1) * (1.f / 64);
+    const float d0 = x0 - mean, d1 = x1 - mean;
+    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64) + 1e-6f);
+    const float xh0 = d0 * rstd, xh1 = d1 * rstd;
+    const float ln0 = ga0 * xh0 + be0, ln1 = ga1 * xh1 + be1;
+    const float ge0 = gelu_erf(ln0), ge1 = gelu_erf(ln1);
+    const float m = mask[static_cast<size_t>(b % maskB) * Ntok + (y / p) * wt + x / p] ? 1.f : 0.f;
+    float dg0 = 0.f, dg1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float pred = warp_sum(w0[c] * ge0 + w1[c] * ge1) + b1[c];
+      const size_t o = (static_cast<size_t>(b) * 3 + c) * plane + yx;
+      const float d = pred - tgts[o];
+      float dl;
+      if (loss_kind == 0) dl = fminf(fmaxf(d * 100.f, -1.f), 1.f);
+      else if (loss_kind == 1) dl = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      else if (loss_kind == 2) dl = 2.f * d;
+      else dl = 0.5f * ((d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + 2.f * d);
+      const float dp = gs * coef[b] * m * valid[o] * dl;
+      dw0[c] += dp * ge0;
+      dw1[c] += dp * ge1;
+      db1[c] += dp;
+      dg0 += dp * w0[c];
+      dg1 += dp * w1[c];
+    }
+    const float dln0 = dg0 * gelu_erf_grad(ln0), dln1 = dg1 * gelu_erf_grad(ln1);
+    dga0 += dln0 * xh0; dga1 += dln1 * xh1;
+    dbe0 += dln0; dbe1 += dln1;
+    const float dx0 = dln0 * ga0, dx1 = dln1 * ga1;
+    const float c1m = warp_sum(dx0 + dx1) * (1.f / 64);
+    const float c2m = warp_sum(dx0 * xh0 + dx1 * xh1) * (1.f / 64);
+    const float o0 = rstd * (dx0 - c1m - xh0 * c2m), o1 = rstd * (dx1 - c1m - xh1 * c2m);
+    reinterpret_cast<uint32_t*>(dc1)[pix * 32 + lane] = pack_bf16x2(o0, o1);
+  }
+  // block reduction through shared memory, then atomics
+  __shared__ float red[8][323];
+  const int wq = threadIdx.x >> 5;
+  red[wq][k0] = dga0; red[wq][k1] = dga1;
+  red[wq][64 + k0] = dbe0; red[wq][64 + k1] = dbe1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    red[wq][128 + c * 64 + k0] = dw0[c];
+    red[wq][128 + c * 64 + k1] = dw1[c];
+  }
+  if (lane == 0) {
+    // db1 is identical across lanes (dp is warp-uniform)
+    red[wq][320] = db1[0]; red[wq][321] = db1[1]; red[wq][322] = db1[2];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 323; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][i];
+    atomicAdd(dhp + 64 + i, s);
+  }
+}
+
+// conv bias gradient: db[o] = sum_pix dC1[pix, o]  (bf16 [npix, 64])  -> reuse the generic column sum
+}  // namespace pk
+
+using namespace pk;
+
+extern "C" int pk_conv3x3_pack(const float* w, void* wf_bf16, void* wd_bf16, void* stream) {
+  PK_CHECK(w && wf_bf16 && wd_bf16, "pk_conv3x3_pack: null pointer");
+  conv_pack_kernel<<<(64 * 576 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(wf_bf16), static_cast<__nv_bfloat16*>(wd_bf16));
+  PK_LAUNCH_CHECK("pk_conv3x3_pack");
+  return 0;
+}
+extern "C" int pk_conv3x3_wgrad_unpack(const float* acc, float* dw, void* stream) {
+  PK_CHECK(acc && dw, "pk_conv3x3_wgrad_unpack: null pointer");
+  conv_wgrad_unpack_kernel<<<(64 * 576 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, dw);
+  PK_LAUNCH_CHECK("pk_conv3x3_wgrad_unpack");
+  return 0;
+}
+extern "C" int pk_loss_prep(const float* tgts, const uint8_t* mask, int maskB, const float* valid,
+                            float* stats_zeroed, int B, int H, int W, int p, void* stream) {
+  PK_CHECK(tgts && mask && valid && stats_zeroed && maskB >= 1, "pk_loss_prep: bad args");
+  dim3 grid(64, B);
+  loss_prep_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(tgts, mask, maskB, valid, stats_zeroed,
+                                                                        H, W, p);
+  PK_LAUNCH_CHECK("pk_loss_prep");
+  return 0;
+}
+extern "C" int pk_loss_finalize(const float* stats, const float* num, float* loss, float* coef, int B,
+                                int seggpt, void* stream) {
+  PK_CHECK(stats && num && loss && coef, "pk_loss_finalize: null pointer");
+  loss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(stats, num, loss, coef, B, seggpt);
+  PK_LAUNCH_CHECK("pk_loss_finalize");
+  return 0;
+}
+extern "C" int pk_decoder_head_bwd(const void* c1, const float* tgts, const uint8_t* mask, int maskB,
+                                   const float* valid, const float* coef, const float* gscale,
+                                   const float* head_params, void* dc1, float* dhead_params_zeroed, int B,
+                                   int H, int W, int p, int loss_kind, void* stream) {
+  PK_CHECK(c1 && tgts && mask && valid && coef && head_params && dc1 && dhead_params_zeroed,
+           "pk_decoder_head_bwd: null pointer");
+  const int grid = sm_count() * 8;
+  head_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(c1), tgts, mask, maskB, valid, coef, gscale, head_params,
+      static_cast<__nv_bfloat16*>(dc1), dhead_params_zeroed, B, H, W, p, loss_kind);
+  PK_LAUNCH_CHECK("pk_decoder_head_bwd");
+  return 0;
+}

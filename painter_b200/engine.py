@@ -1,0 +1,228 @@
+"""Host-side orchestration of the hot path: one torch.autograd.Function per stage (embed, block, merge,
+decoder+loss) so that autograd / DDP hooks fire block by block.  Every arithmetic step is a call into
+libpainter_b200.so (painter_b200/ops.py); torch is used for memory, streams and the autograd tape only.
+
+Stage map (reference file:line -> Function):
+  EmbedFn     Painter/models_painter.py:385-409 (PatchEmbed x2, mask-token blend, segment/pos/type tokens)
+  BlockFn     Painter/models_painter.py:216-235 + Attention :73-89 (+ SegGPT ensemble models_seggpt.py:220-231)
+  MergeFn     Painter/models_painter.py:414-415
+  DecoderFn   Painter/models_painter.py:417 (final LN taps), :420-431 (decoder), :433-462 (loss), :355-368 (patchify)
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_PIXSHUF, EPI_RESID
+
+LOSS_KINDS = {"smoothl1": 0, "l1": 1, "l2": 2, "l1l2": 3}
+
+_bf16_cache = {}
+
+
+def bf16_weight(p, shape2d=None):
+    """bf16 copy of an fp32 parameter, cached on (storage, version): recast only after an optimizer step."""
+    key = id(p)
+    ent = _bf16_cache.get(key)
+    ver = p._version
+    if ent is not None and ent[0] == ver and ent[1] == p.data_ptr():
+        return ent[2]
+    src = p.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    w = ops.cast_bf16(src)
+    if shape2d is not None:
+        w = w.view(shape2d)
+    _bf16_cache[key] = (ver, p.data_ptr(), w)
+    return w
+
+
+def _wgrad(dy_bf16, x_bf16):
+    """dW[out, in] = dY^T . X  (both operands read MN-major; split-K when the tile count is small)."""
+    out = torch.zeros((dy_bf16.shape[1], x_bf16.shape[1]), dtype=torch.float32, device=dy_bf16.device)
+    return ops.gemm(dy_bf16, x_bf16, trans_a=True, trans_b=True, kind=EPI_F32, out=out, accumulate=2)
+
+
+def resize_rel_table(table, size):
+    """vitdet_utils.get_rel_pos (:75-86): linear resize of the table when its length != 2*size-1.
+    Tiny host-side parameter preprocessing; autograd carries the transpose for the backward."""
+    L = 2 * size - 1
+    if table.shape[0] == L:
+        return table
+    return F.interpolate(table.t().unsqueeze(0), size=L, mode="linear")[0].t().contiguous()
+
+
+class EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, imgs, tgts, mask_u8, type_emb, Wp, bp, mask_token, seg_x, seg_y, pos_embed, p, has_cls):
+        B, Cin, H, W = imgs.shape
+        h, w = H // p, W // p
+        N, C = h * w, Wp.shape[0]
+        cols = ops.im2col_patch(imgs, tgts, p)
+        E = ops.gemm(cols, bf16_weight(Wp, (C, Cin * p * p)), kind=EPI_F32, bias=bp)
+        pe = pos_embed[0, 1:] if has_cls else pos_embed[0]
+        s = int(round(pe.shape[0] ** 0.5))
+        assert s * s == pe.shape[0]
+        pe = pe.contiguous()
+        pos = pe if (s == h and s == w) else ops.bicubic_fwd(pe.view(s, s, C), h, w).view(N, C)
+        z = ops.assemble_tokens(E, mask_u8, mask_token.reshape(C).contiguous(), seg_x.reshape(C).contiguous(),
+                                seg_y.reshape(C).contiguous(), pos, type_emb, B, N, C)
+        ctx.save_for_backward(cols, mask_u8)
+        ctx.meta = (B, N, C, h, w, s, has_cls, Wp.shape, pos_embed.shape, mask_token.shape, type_emb is not None)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        cols, mask_u8 = ctx.saved_tensors
+        B, N, C, h, w, s, has_cls, wshape, pshape, tshape, has_type = ctx.meta
+        if has_type and ctx.needs_input_grad[3]:
+            raise NotImplementedError("painter_b200: gradients of the SegGPT type tokens are not implemented "
+                                      "(SegGPT is an inference path, seggpt_engine.py:26)")
+        dz = dz.contiguous()
+        dE, dpos, dsx, dsy, dmt = ops.assemble_tokens_bwd(dz, mask_u8, B, N, C)
+        dW = _wgrad(dE, cols).view(wshape)
+        db = ops.colsum_bf16(dE)
+        dpe = torch.zeros(pshape, dtype=torch.float32, device=dz.device)
+        off = 1 if has_cls else 0
+        if s == h and s == w:
+            dpe[0, off:] = dpos
+        else:
+            dpe[0, off:] = ops.bicubic_bwd(dpos.view(h, w, C), s, s).view(s * s, C)
+        return (None, None, None, None, dW, db, dmt.view(tshape), dsx.view(tshape), dsy.view(tshape), dpe, None,
+                None)
+
+
+class BlockFn(torch.autograd.Function):
+    """x [B'*N, C] fp32 -> same.  meta = (Bp, h, w, heads, eps, ens_groups, ens_P)."""
+
+    @staticmethod
+    def forward(ctx, x, drop_a, drop_m, n1w, n1b, rel_h, rel_w, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w,
+                fc1_b, fc2_w, fc2_b, meta):
+        Bp, h, w, heads, eps, ens_groups, ens_P = meta
+        N = h * w
+        M, C = x.shape
+        u, mean1, rstd1 = ops.layernorm_fwd(x, n1w, n1b, eps)
+        wqkv, wproj = bf16_weight(qkv_w), bf16_weight(proj_w)
+        wfc1, wfc2 = bf16_weight(fc1_w), bf16_weight(fc2_w)
+        qkv = ops.gemm(u, wqkv, kind=EPI_BF16, bias=qkv_b)
+        th = ops.relpos_table_bf16(rel_h.contiguous())
+        tw = ops.relpos_table_bf16(rel_w.contiguous())
+        ao, lse = ops.attn_fwd(qkv, th, tw, Bp, heads, h, w)
+        if ens_groups > 0:
+            a = ops.gemm(ao, wproj, kind=EPI_F32, bias=proj_b)
+            x1 = ops.ensemble_resid(a, x, ens_groups, ens_P, N, C)
+        else:
+            x1 = ops.gemm(ao, wproj, kind=EPI_RESID, bias=proj_b, aux=x, rowscale=drop_a, rows_per_group=N)
+        v, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps)
+        z, hact = ops.gemm(v, wfc1, kind=EPI_GELU, bias=fc1_b)
+        x2 = ops.gemm(hact, wfc2, kind=EPI_RESID, bias=fc2_b, aux=x1, rowscale=drop_m, rows_per_group=N)
+        ctx.save_for_backward(x, mean1, rstd1, u, qkv, ao, lse, th, tw, x1, mean2, rstd2, v, z, hact, wqkv, wproj,
+                              wfc1, wfc2, n1w, n2w, drop_a, drop_m)
+        ctx.meta = meta
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        (x, mean1, rstd1, u, qkv, ao, lse, th, tw, x1, mean2, rstd2, v, z, hact, wqkv, wproj, wfc1, wfc2, n1w, n2w,
+         drop_a, drop_m) = ctx.saved_tensors
+        Bp, h, w, heads, eps, ens_groups, ens_P = ctx.meta
+        if ens_groups > 0:
+            raise NotImplementedError("painter_b200: backward through the SegGPT prompt ensemble is not implemented")
+        N = h * w
+        M, C = x.shape
+        dev = x.device
+        dx2 = dx2.contiguous()
+        # ---- MLP branch ----
+        dy, dfc2_b = ops.scale_cast_colsum(dx2, drop_m, N)
+        dfc2_w = _wgrad(dy, hact)
+        dz = ops.gemm(dy, wfc2, trans_b=True, kind=EPI_DGELU, aux=z)
+        dfc1_b = ops.colsum_bf16(dz)
+        dfc1_w = _wgrad(dz, v)
+        dv = ops.gemm(dz, wfc1, trans_b=True, kind=EPI_F32)
+        dn2w = torch.zeros(C, dtype=torch.float32, device=dev)
+        dn2b = torch.zeros(C, dtype=torch.float32, device=dev)
+        dx1 = ops.layernorm_bwd(dv, x1, mean2, rstd2, n2w, dn2w, dn2b, dres=dx2)
+        # ---- attention branch ----
+        da, dproj_b = ops.scale_cast_colsum(dx1, drop_a, N)
+        dproj_w = _wgrad(da, ao)
+        dao = ops.gemm(da, wproj, trans_b=True, kind=EPI_BF16)
+        dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bp, heads, h, w)
+        dqkv_b = ops.colsum_bf16(dqkv)
+        dqkv_w = _wgrad(dqkv, u)
+        du = ops.gemm(dqkv, wqkv, trans_b=True, kind=EPI_F32)
+        dn1w = torch.zeros(C, dtype=torch.float32, device=dev)
+        dn1b = torch.zeros(C, dtype=torch.float32, device=dev)
+        dx = ops.layernorm_bwd(du, x, mean1, rstd1, n1w, dn1w, dn1b, dres=dx1)
+        return (dx, None, None, dn1w, dn1b, dTh, dTw, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b,
+                dfc2_w, dfc2_b, None)
+
+
+class MergeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        return ops.merge_halves(z)
+
+    @staticmethod
+    def backward(ctx, d):
+        return ops.merge_halves_bwd(d.contiguous())
+
+
+class DecoderFn(torch.autograd.Function):
+    """(4 tap activations) -> (loss[1], patchified prediction [B, N, p*p*3])."""
+
+    @staticmethod
+    def forward(ctx, t0, t1, t2, t3, norm_w, norm_b, dec_w, dec_b, c3_w, c3_b, ln_w, ln_b, c1_w, c1_b, tgts, mask_u8,
+                valid, meta):
+        B, h, w, p, eps, loss_kind, seggpt = meta
+        M, C = t0.shape
+        dev = t0.device
+        dd = ln_w.shape[0]
+        if dd != 64:
+            raise NotImplementedError("painter_b200: decoder_embed_dim must be 64 (the stock configuration)")
+        taps = (t0, t1, t2, t3)
+        cat = torch.empty((M, 4 * C), dtype=torch.bfloat16, device=dev)
+        stats = []
+        for k, t in enumerate(taps):
+            _, mean, rstd = ops.layernorm_fwd(t, norm_w, norm_b, eps, out=cat[:, k * C:(k + 1) * C])
+            stats.append((mean, rstd))
+        wdec = bf16_weight(dec_w)
+        g = torch.empty((B, h * p, w * p, dd), dtype=torch.bfloat16, device=dev)
+        ops.gemm(cat, wdec, kind=EPI_PIXSHUF, bias=dec_b, pixshuf=(h, w, p, dd, g))
+        wf, wd = ops.conv3x3_pack(c3_w.contiguous())
+        hp = torch.cat([c3_b, ln_w, ln_b, c1_w.reshape(-1), c1_b, c1_b.new_zeros(5)]).contiguous()
+        st = ops.loss_prep(tgts, mask_u8, valid, p)
+        c1, patch, num = ops.decoder_head_fwd(g, wf, hp, tgts, mask_u8, valid, p, loss_kind)
+        loss, coef = ops.loss_finalize(st, num, seggpt)
+        ctx.save_for_backward(t0, t1, t2, t3, norm_w, cat, wdec, g, wd, hp, c1, tgts, mask_u8, valid, coef,
+                              *[s for pair in stats for s in pair])
+        ctx.meta = meta
+        ctx.shapes = (c3_w.shape, c1_w.shape)
+        ctx.mark_non_differentiable(patch)
+        return loss, patch
+
+    @staticmethod
+    def backward(ctx, dloss, _dpatch):
+        sv = ctx.saved_tensors
+        t = sv[0:4]
+        norm_w, cat, wdec, g, wd, hp, c1, tgts, mask_u8, valid, coef = sv[4:15]
+        stats = sv[15:]
+        B, h, w, p, eps, loss_kind, seggpt = ctx.meta
+        M, C = t[0].shape
+        dev = c1.device
+        gscale = dloss.reshape(1).to(torch.float32).contiguous()
+        dc1, dhp = ops.decoder_head_bwd(c1, tgts, mask_u8, valid, coef, gscale, hp, p, loss_kind)
+        dc3_b = ops.colsum_bf16(dc1.view(-1, 64))
+        dc3_w = ops.conv3x3_wgrad(g, dc1)
+        dD = ops.conv3x3_dgrad_unshuffle(dc1, wd, p)          # [M, p*p*64] bf16, token-major
+        ddec_b = ops.colsum_bf16(dD)
+        ddec_w = _wgrad(dD, cat)
+        dcat = ops.gemm(dD, wdec, trans_b=True, kind=EPI_F32)  # [M, 4C] fp32
+        dnw = torch.zeros(C, dtype=torch.float32, device=dev)
+        dnb = torch.zeros(C, dtype=torch.float32, device=dev)
+        dts = []
+        for k in range(4):
+            dts.append(ops.layernorm_bwd(dcat[:, k * C:(k + 1) * C], t[k], stats[2 * k], stats[2 * k + 1], norm_w,
+                                         dnw, dnb))
+        c3shape, c1shape = ctx.shapes
+        return (dts[0], dts[1], dts[2], dts[3], dnw, dnb, ddec_w, ddec_b, dc3_w, dc3_b, dhp[64:128].clone(),
+                dhp[128:192].clone(), dhp[192:384].reshape(c1shape).clone(), dhp[384:387].clone(), None, None, None,
+                None)

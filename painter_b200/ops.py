@@ -82,7 +82,7 @@ def gemm(a, b, *, trans_a=False, trans_b=False, kind=EPI_BF16, out=None, out2=No
         e.rowscale = rowscale.data_ptr()
         e.rows_per_group = rows_per_group
     e.alpha = alpha
-    e.accumulate = 1 if accumulate else 0
+    e.accumulate = int(accumulate)  # 0 overwrite, 1 read-modify-write, 2 zero-initialised + split-K atomics
     check(lib().pk_gemm_bf16(_ptr(a), _ptr(b), M, N, K, a.stride(0), b.stride(0), int(trans_a),
                              int(trans_b), ctypes.byref(e), _stream()), "pk_gemm_bf16")
     if kind == EPI_GELU:
@@ -116,3 +116,215 @@ def attn_fwd(qkv, th, tw, B, heads, h, w, need_lse=True):
     check(lib().pk_attn_fwd(_ptr(qkv), _ptr(th), _ptr(tw), _ptr(out), _ptr(lse), B, heads, h, w,
                             th.shape[0], tw.shape[0], _stream()), "pk_attn_fwd")
     return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None):
+    """Fused attention backward.  Returns (dqkv bf16 [B*N, 3C], dTh fp32 [2h-1, 64], dTw fp32 [2w-1, 64])."""
+    N, C = h * w, heads * 64
+    _req(dout, torch.bfloat16, "dout")
+    assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
+    dev = qkv.device
+    dqkv = torch.empty_like(qkv)
+    dTh = torch.zeros((2 * h - 1, 64), dtype=torch.float32, device=dev)
+    dTw = torch.zeros((2 * w - 1, 64), dtype=torch.float32, device=dev)
+    delta = torch.empty((B * heads * N,), dtype=torch.float32, device=dev)
+    relh_g = torch.empty((B * heads * N * h,), dtype=torch.float32, device=dev)
+    relw_g = torch.empty((B * heads * N * w,), dtype=torch.float32, device=dev)
+    check(lib().pk_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(th), _ptr(tw), _ptr(dqkv),
+                            _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), B, heads, h, w,
+                            th.shape[0], tw.shape[0], _stream()), "pk_attn_bwd")
+    return dqkv, dTh, dTw
+
+
+# --------------------------------------------------------------------------------------------------
+# bandwidth kernels
+# --------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, out=None, out_dtype=torch.bfloat16, want_stats=True):
+    """x fp32 [M, C] (row stride free) -> LN(x) (bf16 or fp32, may be a column slice of a wider buffer)."""
+    _req(x, torch.float32, "x")
+    M, C = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, C), dtype=out_dtype, device=x.device)
+    assert out.stride(1) == 1 and tuple(out.shape) == (M, C)
+    mean = torch.empty((M,), dtype=torch.float32, device=x.device) if want_stats else None
+    rstd = torch.empty((M,), dtype=torch.float32, device=x.device) if want_stats else None
+    check(lib().pk_layernorm_fwd(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), ctypes.c_float(eps), _ptr(out),
+                                 out.stride(0), int(out.dtype == torch.bfloat16), _ptr(mean), _ptr(rstd), M, C,
+                                 _stream()), "pk_layernorm_fwd")
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
+    """Returns dx fp32 [M, C] (+ dres); accumulates into dgamma / dbeta (fp32, caller-initialised)."""
+    _req(dy, torch.float32, "dy")
+    _req(x, torch.float32, "x")
+    M, C = x.shape
+    assert dy.stride(1) == 1 and x.stride(1) == 1
+    dx = torch.empty((M, C), dtype=torch.float32, device=x.device)
+    if dres is not None:
+        assert dres.is_contiguous()
+    check(lib().pk_layernorm_bwd(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma),
+                                 _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), M, C, _stream()),
+          "pk_layernorm_bwd")
+    return dx
+
+
+def im2col_patch(imgs, tgts, p):
+    _req(imgs, torch.float32, "imgs")
+    _req(tgts, torch.float32, "tgts")
+    assert imgs.is_contiguous() and tgts.is_contiguous() and imgs.shape == tgts.shape
+    B, Cin, H, W = imgs.shape
+    out = torch.empty((2 * B * (H // p) * (W // p), Cin * p * p), dtype=torch.bfloat16, device=imgs.device)
+    check(lib().pk_im2col_patch(_ptr(imgs), _ptr(tgts), _ptr(out), B, Cin, H, W, p, _stream()), "pk_im2col_patch")
+    return out
+
+
+def assemble_tokens(E, mask_u8, mask_token, seg_x, seg_y, pos, type_emb, B, N, C):
+    out = torch.empty_like(E)
+    check(lib().pk_assemble_tokens(_ptr(E), _ptr(mask_u8), mask_u8.shape[0], _ptr(mask_token), _ptr(seg_x),
+                                   _ptr(seg_y), _ptr(pos), _ptr(type_emb), _ptr(out), B, N, C, _stream()),
+          "pk_assemble_tokens")
+    return out
+
+
+def assemble_tokens_bwd(dZ, mask_u8, B, N, C):
+    dev = dZ.device
+    dE = torch.empty((2 * B * N, C), dtype=torch.bfloat16, device=dev)
+    dpos = torch.empty((N, C), dtype=torch.float32, device=dev)
+    small = torch.zeros((3, C), dtype=torch.float32, device=dev)
+    check(lib().pk_assemble_tokens_bwd(_ptr(dZ), _ptr(mask_u8), mask_u8.shape[0], _ptr(dE), _ptr(dpos),
+                                       _ptr(small[0]), _ptr(small[1]), _ptr(small[2]), B, N, C, _stream()),
+          "pk_assemble_tokens_bwd")
+    return dE, dpos, small[0], small[1], small[2]
+
+
+def bicubic_fwd(src, h, w):
+    """src fp32 [s, s, C] -> [h, w, C]  (F.interpolate bicubic, align_corners=False)."""
+    sh, sw, C = src.shape
+    out = torch.empty((h, w, C), dtype=torch.float32, device=src.device)
+    check(lib().pk_bicubic_fwd(_ptr(src), _ptr(out), sh, sw, h, w, C, _stream()), "pk_bicubic_fwd")
+    return out
+
+
+def bicubic_bwd(dout, sh, sw):
+    h, w, C = dout.shape
+    dsrc = torch.zeros((sh, sw, C), dtype=torch.float32, device=dout.device)
+    check(lib().pk_bicubic_bwd(_ptr(dout), _ptr(dsrc), sh, sw, h, w, C, _stream()), "pk_bicubic_bwd")
+    return dsrc
+
+
+def merge_halves(z):
+    half = z.shape[0] // 2
+    out = torch.empty((half,) + tuple(z.shape[1:]), dtype=torch.float32, device=z.device)
+    check(lib().pk_merge_halves(_ptr(z), _ptr(out), ctypes.c_longlong(out.numel()), _stream()), "pk_merge_halves")
+    return out
+
+
+def merge_halves_bwd(d):
+    out = torch.empty((2 * d.shape[0],) + tuple(d.shape[1:]), dtype=torch.float32, device=d.device)
+    check(lib().pk_merge_halves_bwd(_ptr(d), _ptr(out), ctypes.c_longlong(d.numel()), _stream()),
+          "pk_merge_halves_bwd")
+    return out
+
+
+def cast_bf16(x):
+    _req(x, torch.float32, "x")
+    assert x.is_contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().pk_cast_bf16(_ptr(x), _ptr(out), ctypes.c_longlong(x.numel()), _stream()), "pk_cast_bf16")
+    return out
+
+
+def scale_cast_colsum(x, rowscale=None, rows_per_group=0, want_colsum=True):
+    """fp32 [M, C] -> (bf16 [M, C] scaled per row group, column sums fp32 [C])."""
+    _req(x, torch.float32, "x")
+    M, C = x.shape
+    out = torch.empty((M, C), dtype=torch.bfloat16, device=x.device)
+    cs = torch.zeros((C,), dtype=torch.float32, device=x.device) if want_colsum else None
+    check(lib().pk_scale_cast_colsum(_ptr(x), x.stride(0), _ptr(rowscale), rows_per_group, _ptr(out), _ptr(cs), M, C,
+                                     _stream()), "pk_scale_cast_colsum")
+    return out, cs
+
+
+def colsum_bf16(x, ncols=None):
+    _req(x, torch.bfloat16, "x")
+    M, C = x.shape
+    cs = torch.zeros((C,), dtype=torch.float32, device=x.device)
+    check(lib().pk_colsum_bf16(_ptr(x), x.stride(0), _ptr(cs), M, C, _stream()), "pk_colsum_bf16")
+    return cs
+
+
+def ensemble_resid(a, z, G, P, N, C):
+    out = torch.empty_like(z)
+    check(lib().pk_ensemble_resid(_ptr(a), _ptr(z), _ptr(out), G, P, N, C, _stream()), "pk_ensemble_resid")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# decoder head
+# --------------------------------------------------------------------------------------------------
+def conv3x3_pack(w):
+    _req(w, torch.float32, "w")
+    assert tuple(w.shape) == (64, 64, 3, 3) and w.is_contiguous()
+    wf = torch.empty((64, 576), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((64, 576), dtype=torch.bfloat16, device=w.device)
+    check(lib().pk_conv3x3_pack(_ptr(w), _ptr(wf), _ptr(wd), _stream()), "pk_conv3x3_pack")
+    return wf, wd
+
+
+def loss_prep(tgts, mask_u8, valid, p):
+    B, _, H, W = tgts.shape
+    stats = torch.zeros((B, 2), dtype=torch.float32, device=tgts.device)
+    check(lib().pk_loss_prep(_ptr(tgts), _ptr(mask_u8), mask_u8.shape[0], _ptr(valid), _ptr(stats), B, H, W, p,
+                             _stream()), "pk_loss_prep")
+    return stats
+
+
+def decoder_head_fwd(g_nhwc, wf, head_params, tgts, mask_u8, valid, p, loss_kind):
+    B, H, W, c = g_nhwc.shape
+    assert c == 64 and g_nhwc.is_contiguous()
+    dev = g_nhwc.device
+    c1 = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=dev)
+    patch = torch.empty((B, (H // p) * (W // p), p * p * 3), dtype=torch.float32, device=dev)
+    num = torch.zeros((B,), dtype=torch.float32, device=dev)
+    check(lib().pk_decoder_head_fwd(_ptr(g_nhwc), _ptr(wf), _ptr(head_params), _ptr(tgts), _ptr(mask_u8),
+                                    mask_u8.shape[0], _ptr(valid), _ptr(c1), _ptr(patch), _ptr(num), B, H, W, p,
+                                    loss_kind, _stream()), "pk_decoder_head_fwd")
+    return c1, patch, num
+
+
+def loss_finalize(stats, num, seggpt):
+    B = num.shape[0]
+    loss = torch.empty((1,), dtype=torch.float32, device=num.device)
+    coef = torch.empty((B,), dtype=torch.float32, device=num.device)
+    check(lib().pk_loss_finalize(_ptr(stats), _ptr(num), _ptr(loss), _ptr(coef), B, int(seggpt), _stream()),
+          "pk_loss_finalize")
+    return loss, coef
+
+
+def decoder_head_bwd(c1, tgts, mask_u8, valid, coef, gscale, head_params, p, loss_kind):
+    B, H, W, _ = c1.shape
+    dc1 = torch.empty_like(c1)
+    dhp = torch.zeros((392,), dtype=torch.float32, device=c1.device)
+    check(lib().pk_decoder_head_bwd(_ptr(c1), _ptr(tgts), _ptr(mask_u8), mask_u8.shape[0], _ptr(valid), _ptr(coef),
+                                    _ptr(gscale), _ptr(head_params), _ptr(dc1), _ptr(dhp), B, H, W, p, loss_kind,
+                                    _stream()), "pk_decoder_head_bwd")
+    return dc1, dhp
+
+
+def conv3x3_dgrad_unshuffle(dc1, wd, p):
+    B, H, W, _ = dc1.shape
+    out = torch.empty((B * (H // p) * (W // p), p * p * 64), dtype=torch.bfloat16, device=dc1.device)
+    check(lib().pk_conv3x3_dgrad_unshuffle(_ptr(dc1), _ptr(wd), _ptr(out), B, H, W, p, _stream()),
+          "pk_conv3x3_dgrad_unshuffle")
+    return out
+
+
+def conv3x3_wgrad(g_nhwc, dc1):
+    B, H, W, _ = dc1.shape
+    acc = torch.zeros((640, 64), dtype=torch.float32, device=dc1.device)
+    check(lib().pk_conv3x3_wgrad(_ptr(g_nhwc), _ptr(dc1), _ptr(acc), B, H, W, _stream()), "pk_conv3x3_wgrad")
+    dw = torch.empty((64, 64, 3, 3), dtype=torch.float32, device=dc1.device)
+    check(lib().pk_conv3x3_wgrad_unpack(_ptr(acc), _ptr(dw), _stream()), "pk_conv3x3_wgrad_unpack")
+    return dw

@@ -18,7 +18,7 @@ CASES = [
     ("one_tile_4x28", 1, 1, 4, 28),
     ("mid_56x28", 1, 2, 56, 28),
     ("h_16x8", 2, 1, 16, 8),
-    ("long_112x56", 1, 2, 112, 56),
+    ("long_112x56", 1, 1, 112, 56),
     ("full_b8", 8, 16, 56, 28),
     ("full_b16", 16, 16, 56, 28),
 ]
@@ -43,6 +43,48 @@ def ref_attn(qkv, th, tw, B, heads, h, w):
     return o, lse.reshape(B * heads, N)
 
 
+def check_bwd(res, qkv, th, tw, out, lse, B, heads, h, w):
+    """Backward vs torch autograd through the fp32 reference (on bf16-rounded inputs)."""
+    import torch
+    from painter_b200 import ops
+    N, C = h * w, heads * 64
+    dout = (torch.randn(B * N, C, device=qkv.device) * 0.5).bfloat16()
+    dqkv, dTh, dTw = ops.attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w)
+    torch.cuda.synchronize()
+    if B * heads * N * N <= 2 ** 26:
+        q32 = qkv.float().requires_grad_(True)
+        th32 = th.float().requires_grad_(True)
+        tw32 = tw.float().requires_grad_(True)
+        ro, _ = ref_attn(q32, th32, tw32, B, heads, h, w)
+        (ro * dout.float()).sum().backward()
+        def rel(a, b):
+            return ((a.float() - b).abs().max() / b.abs().max().clamp_min(1e-9)).item()
+        g = q32.grad.reshape(B * N, 3, C)
+        d = dqkv.float().reshape(B * N, 3, C)
+        res["dq_err"] = rel(d[:, 0], g[:, 0])
+        res["dk_err"] = rel(d[:, 1], g[:, 1])
+        res["dv_err"] = rel(d[:, 2], g[:, 2])
+        res["dTh_err"] = rel(dTh, th32.grad[: 2 * h - 1])
+        res["dTw_err"] = rel(dTw, tw32.grad[: 2 * w - 1])
+        res["bwd_ok"] = bool(max(res["dq_err"], res["dk_err"], res["dv_err"], res["dTh_err"], res["dTw_err"]) < 3e-2)
+        res["ok"] = bool(res.get("ok", True) and res["bwd_ok"])
+    else:
+        res["bwd_finite"] = bool(torch.isfinite(dqkv.float()).all().item() and torch.isfinite(dTh).all().item())
+    if B * heads * N * N >= 2 ** 27:
+        for _ in range(3):
+            ops.attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        res["bwd_ms"] = ms
+        res["bwd_tflops"] = 10.0 * B * heads * N * N * 64 / ms / 1e9
+
+
 def run_case(name, B, heads, h, w):
     import torch
     from painter_b200 import ops
@@ -55,6 +97,18 @@ def run_case(name, B, heads, h, w):
     out, lse = ops.attn_fwd(qkv, th, tw, B, heads, h, w)
     torch.cuda.synchronize()
     res = {"case": name, "B": B, "heads": heads, "h": h, "w": w}
+    try:
+        _run_fwd_checks(res, qkv, th, tw, out, lse, B, heads, h, w)
+    finally:
+        pass
+    check_bwd(res, qkv, th, tw, out, lse, B, heads, h, w)
+    return res
+
+
+def _run_fwd_checks(res, qkv, th, tw, out, lse, B, heads, h, w):
+    import torch
+    from painter_b200 import ops
+    N, C = h * w, heads * 64
     if B * heads * N * N <= 2 ** 28:
         ro, rl = ref_attn(qkv, th, tw, B, heads, h, w)
         res["out_err"] = ((out.float() - ro).abs().max() / ro.abs().max()).item()
@@ -79,7 +133,6 @@ def run_case(name, B, heads, h, w):
         ms = e0.elapsed_time(e1) / 10
         res["ms"] = ms
         res["tflops"] = 4.0 * B * heads * N * N * 64 / ms / 1e9
-    return res
 
 
 if __name__ == "__main__":

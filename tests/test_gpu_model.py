@@ -1,0 +1,150 @@
+"""GPU parity of the painter_b200 modules against (i) golden vectors produced by the UNMODIFIED reference and
+(ii) the CPU oracle.  Tolerances (bf16 tensor-core operands, fp32 accumulate; SURVEY.md section 8c calibration:
+the reference's own bf16-vs-fp32 noise is loss 4e-7, logits RMS 9.5e-3 / max 1.3e-2, grads RMS 1.1e-2):
+   loss   rel <= 2e-3        logits  rms-rel <= 1.5e-2, max-rel <= 4e-2        grads  rms-rel <= 4e-2
+"""
+import pytest
+import torch
+
+from oracle import painter_oracle as po
+from oracle.synth import synth_inputs, synth_state_dict
+
+from _common import build_model, load_golden, rel_max, rel_rms
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL, LOGIT_RMS, LOGIT_MAX, GRAD_RMS = 2e-3, 1.5e-2, 4e-2, 4e-2
+
+
+def _to(dev, *ts):
+    return [t.to(dev) for t in ts]
+
+
+def _check_grads(model, ref_grads, ref_norms=None):
+    named = dict(model.named_parameters())
+    bad = []
+    for k, g in ref_grads.items():
+        e = rel_rms(named[k].grad, g)
+        if e > GRAD_RMS:
+            bad.append((k, e))
+    if ref_norms is not None:
+        for k, n in ref_norms.items():
+            gn = named[k].grad.float().norm().item()
+            if abs(gn - n) > 0.05 * max(n, 1e-5) + 1e-6:
+                bad.append((k + "(norm)", gn, n))
+    assert not bad, bad[:10]
+
+
+def test_painter_tiny_eval_fwd_bwd_vs_reference_golden():
+    gold = load_golden("painter_tiny.pt")
+    cfg = po.PainterConfig(**gold["cfg"])
+    model, _ = build_model(cfg, gold["weight_seed"])
+    model.eval()
+    imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, **gold["inputs"]))
+    loss, pred, m = model(imgs, tgts, mask, valid)
+    ev = gold["eval"]
+    assert abs(loss.item() - ev["loss"].item()) <= LOSS_TOL * abs(ev["loss"].item())
+    assert rel_rms(pred, ev["pred"]) <= LOGIT_RMS and rel_max(pred, ev["pred"]) <= LOGIT_MAX
+    assert torch.equal(m.cpu(), ev["mask"])
+    loss.backward()
+    _check_grads(model, ev["grads"], ev["grad_norms"])
+
+
+def test_painter_tiny_train_mode_droppath_replay():
+    gold = load_golden("painter_tiny.pt")
+    cfg = po.PainterConfig(**gold["cfg"])
+    model, _ = build_model(cfg, gold["weight_seed"])
+    model.train()
+    imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, **gold["inputs"]))
+    torch.manual_seed(gold["train_seed"])
+    drops = po.draw_drop_scales(cfg, imgs.shape[0])  # the reference's CPU draws, replayed
+    it = iter(drops)
+    model._drop_scales = lambda i, Bp, dev: tuple(t.to(dev) for t in drops[i])
+    loss, pred, _ = model(imgs, tgts, mask, valid)
+    tr = gold["train"]
+    assert abs(loss.item() - tr["loss"].item()) <= LOSS_TOL * abs(tr["loss"].item())
+    assert rel_rms(pred, tr["pred"]) <= LOGIT_RMS
+    loss.backward()
+    _check_grads(model, tr["grads"], tr["grad_norms"])
+
+
+def test_painter_tiny_interpolated_tables():
+    """64x32 input on the 128x64 model: abs-pos bicubic + rel-pos linear resize (vitdet_utils.py:75-86,141-153)."""
+    gold = load_golden("painter_tiny.pt")
+    cfg = po.PainterConfig(**gold["cfg"])
+    model, _ = build_model(cfg, gold["weight_seed"])
+    model.eval()
+    it = gold["interp"]
+    i2, t2, mk2, v2 = _to("cuda", *synth_inputs(cfg, **it["inputs"]))
+    with torch.no_grad():
+        loss, pred, _ = model(i2, t2, mk2, v2)
+    assert abs(loss.item() - it["loss"].item()) <= LOSS_TOL * abs(it["loss"].item())
+    assert rel_rms(pred, it["pred"]) <= LOGIT_RMS
+
+
+def test_seggpt_tiny_prompts_and_ensemble():
+    gold = load_golden("seggpt_tiny.pt")
+    cfg = po.PainterConfig(**gold["cfg"])
+    model, _ = build_model(cfg, gold["weight_seed"])
+    model.eval()
+    h, w = cfg.grid
+    for c in gold["cases"]:
+        x, t, _, _ = synth_inputs(cfg, c["P"], c["seed"])
+        bm = torch.zeros(1, h * w)
+        bm[:, h * w // 2:] = 1
+        seg = torch.full((c["P"], 1), float(c["seg_type"]))
+        with torch.no_grad():
+            loss, pred, _ = model(x.cuda(), t.cuda(), bm.cuda(), torch.ones_like(t).cuda(), seg.cuda(),
+                                  c["merge_between_batch"])
+        assert abs(loss.item() - c["loss"].item()) <= LOSS_TOL * abs(c["loss"].item()), c["P"]
+        assert rel_rms(pred, c["pred"]) <= LOGIT_RMS, c["P"]
+
+
+def test_full_size_forward_vs_oracle():
+    """ViT-L 896x448, B=1, eval forward against the CPU oracle (fp32) on the same seeded weights/inputs."""
+    cfg = po.PainterConfig()
+    model, sd = build_model(cfg, 1)
+    model.eval()
+    imgs, tgts, mask, valid = synth_inputs(cfg, 1, 21)
+    with torch.no_grad():
+        loss, pred, _ = model(imgs.cuda(), tgts.cuda(), mask.cuda(), valid.cuda())
+        torch.set_num_threads(max(1, torch.get_num_threads()))
+        rl, rp, _ = po.forward(sd, cfg, imgs, tgts, mask, valid)
+    assert abs(loss.item() - rl.item()) <= LOSS_TOL * abs(rl.item())
+    assert rel_rms(pred, rp) <= LOGIT_RMS and rel_max(pred, rp) <= LOGIT_MAX
+
+
+def test_amp_gradscaler_training_steps_like_engine_train():
+    """The step of engine_train.train_one_epoch (:56-93) + misc.NativeScalerWithGradNormCount (:252-269):
+    fp16-autocast context, GradScaler, grad clipping, AdamW — must run and reduce the loss."""
+    cfg = po.PainterConfig(img_size=(128, 64), embed_dim=128, num_heads=2, decoder_embed_dim=64)
+    model, _ = build_model(cfg, 0)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.05)
+    scaler = torch.cuda.amp.GradScaler()
+    imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, 4, 3))
+    losses = []
+    for step in range(6):
+        with torch.cuda.amp.autocast():
+            loss, y, m = model(imgs, tgts, bool_masked_pos=mask, valid=valid)
+        losses.append(loss.item())
+        assert torch.isfinite(loss)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        norm = torch.nn.utils.clip_grad_norm_(model.parameters(), 3.0)
+        assert torch.isfinite(norm)
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad()
+    assert losses[-1] < losses[0], losses
+
+
+def test_no_cpu_fallback():
+    cfg = po.PainterConfig(img_size=(128, 64), embed_dim=128, num_heads=2, decoder_embed_dim=64)
+    from functools import partial
+    from painter_b200 import models_painter
+    m = models_painter.Painter(img_size=(128, 64), embed_dim=128, num_heads=2, decoder_embed_dim=64,
+                               use_rel_pos=True, depth=24, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    x = torch.randn(1, 3, 128, 64)
+    with pytest.raises(RuntimeError):
+        m(x, x, torch.zeros(1, 8, 4), torch.ones(1, 3, 128, 64))

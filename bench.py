@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the ViT-L 896x448 MIM training step (BASELINE.json configs[1]: bf16, batch 8
+per GPU) through painter_b200, at N GPUs of one node (weak scaling: global batch 8*N, DDP over NCCL).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle port) on host cores
+
+One step = forward + backward (+ DDP gradient all-reduce) + fused AdamW update on one synthetic batch.
+`value` is timed with the batch already resident in HBM; `e2e` is the same step through the public module API with
+the batch copied from pinned host memory and the loss read back every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_IMAGE_TRAIN = 4769.23e9   # forward 1589.74 GF, train = 3x
+BATCH_PER_GPU = 8
+H, W = 896, 448
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md sustained bf16)"
+
+
+def _masks(B, seed):
+    """BEiT block masks drawn by the reference MaskingGenerator (fixture made by oracle/make_golden.py)."""
+    import numpy as np
+    import torch
+    packed = torch.load(os.path.join(ROOT, "tests", "golden", "beit_masks_56x28.pt"), weights_only=False).numpy()
+    m = np.unpackbits(packed, axis=-1)[..., :28]
+    idx = [(seed * 7 + i) % m.shape[0] for i in range(B)]
+    return torch.from_numpy(m[idx].astype("int32"))
+
+
+def _batch(B, seed):
+    import torch
+    g = torch.Generator().manual_seed(1234 + seed)
+    imgs = torch.randn(B, 3, H, W, generator=g)
+    tgts = torch.randn(B, 3, H, W, generator=g)
+    return imgs, tgts, _masks(B, seed), torch.ones(B, 3, H, W)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_step_time(threads, reps=1):
+    """Oracle port (torch-CPU fp32 restatement of the reference), B=1 896x448 train step (fwd + bwd)."""
+    import torch
+    from oracle import painter_oracle as po
+    from oracle.synth import synth_state_dict
+    torch.set_num_threads(threads)
+    cfg = po.PainterConfig()
+    sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(cfg, 0).items()}
+    imgs, tgts, mask, valid = _batch(1, 0)
+    times = []
+    for _ in range(reps):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        drops = po.draw_drop_scales(cfg, 1)
+        loss, _, _ = po.forward(sd, cfg, imgs, tgts, mask, valid, drops=drops)
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = min(os.cpu_count() or 1, 32)   # beyond ~32 threads torch-CPU eager slows down (oversubscription)
+    t = cpu_port_step_time(threads, reps=args.warmup + args.steps)[args.warmup:]
+    ms = 1e3 * sum(t) / len(t)
+    val = 1.0 / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "images/sec ViT-L 896x448 MIM train step", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-L 896x448 MIM train step (fwd+bwd), B=1 per step on host cores",
+                   "global_batch": 1, "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} x (B=1 forward+backward) of the oracle port, torch-CPU fp32"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="diagnostic only; the reported step includes AdamW")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from painter_b200 import _lib, models_painter, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    W_steps = max(args.warmup, 3)
+    B = args.batch
+
+    torch.manual_seed(0)
+    model = models_painter.painter_vit_large_patch16_input896x448_win_dec64_8glb_sl1().to(dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "rel_pos" in n:
+                p.normal_(std=0.02)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, fused=True)
+
+    host = [t.pin_memory() for t in _batch(B, rank)]
+    resident = [t.to(dev) for t in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+
+    # per-launch timing of the dominant kernel (the tcgen05 GEMM) with CUDA events on the launching stream
+    gemm_log = []
+    orig_gemm = ops.gemm
+    record = {"on": False}
+
+    def timed_gemm(a, b, *aa, **kw):
+        if not record["on"]:
+            return orig_gemm(a, b, *aa, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_gemm(a, b, *aa, **kw)
+        e1.record()
+        M = a.shape[1] if kw.get("trans_a") else a.shape[0]
+        K = a.shape[0] if kw.get("trans_a") else a.shape[1]
+        N = b.shape[1] if kw.get("trans_b") else b.shape[0]
+        gemm_log.append((2.0 * M * N * K, e0, e1))
+        return out
+
+    ops.gemm = timed_gemm
+    import painter_b200.engine as eng
+    eng.ops.gemm = timed_gemm
+
+    def step(batch, read_loss):
+        imgs, tgts, mask, valid = batch
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, _, _ = net(imgs, tgts, bool_masked_pos=mask, valid=valid)
+        loss.backward()
+        if not args.no_optimizer:
+            opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.item() if read_loss else None
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W_steps):
+        step(resident, False)
+    sync()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    # ---------------- timed region 1: device-resident inputs ----------------
+    record["on"] = True
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        step(resident, False)
+    e1.record()
+    sync()
+    launches = _lib.launch_count() - n0
+    record["on"] = False
+    ms_total = e0.elapsed_time(e1)
+    # ---------------- timed region 2: end to end (pinned host -> device every step, loss read back) ----------------
+    last_loss = None
+    sync()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        batch = [t.to(dev, non_blocking=True) for t in host]
+        last_loss = step(batch, True)
+    e3.record()
+    sync()
+    ms_e2e = e2.elapsed_time(e3)
+    clk = clocks.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+    e2e_val = world * B / (ms_e2e / args.steps / 1e3)
+
+    if rank == 0:
+        flops = sum(f for f, _, _ in gemm_log)
+        gms = sum(a.elapsed_time(b) for _, a, b in gemm_log)
+        peak, peak_src = _peaks()
+        achieved = flops / (gms / 1e3) / 1e12 if gms > 0 else 0.0
+        line = {
+            "metric": "images/sec ViT-L 896x448 MIM train step", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W_steps, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ViT-L 896x448 bf16 MIM train step (fwd+bwd+AdamW), batch 8 per GPU "
+                                   "(BASELINE.json configs[1]; configs[3] at 8 GPUs)",
+                       "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "tokens_per_image": 1568, "optimizer": "none" if args.no_optimizer else "AdamW(fused)",
+                       "l2": "per-step working set (1.5 GB weights + >10 GB activations) far exceeds the 126 MB L2; "
+                             "no explicit flush"},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "pk::gemm_bf16_kernel (tcgen05 GEMM, all linear layers fwd/bwd)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "peak_source": peak_src,
+                         "launches": len(gemm_log), "share_of_step": gms / ms_total, "traffic": None,
+                         "step_mfu": value / world * FLOPS_PER_IMAGE_TRAIN / 1e12 / peak},
+            "clocks": clk, "loss": last_loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = min(os.cpu_count() or 1, 32)
+            ts = cpu_port_step_time(threads, reps=1)
+            line["cpu_baseline"] = {"value": 1.0 / ts[-1], "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": "1 x (B=1 forward+backward) of the oracle port, torch-CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

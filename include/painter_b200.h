@@ -56,13 +56,108 @@ typedef struct {
   int ldc;            /* row stride of out/out2 (elements) */
   int ld_aux;         /* row stride of aux (elements) */
   int rows_per_group; /* rows sharing one rowscale entry */
-  int accumulate;
+  int accumulate;     /* PK_EPI_F32: 0 overwrite, 1 out += , 2 out zero-initialised, split-K atomics */
   float alpha;
   int ps_h, ps_w, ps_p, ps_c; /* pixel shuffle geometry: token grid h x w, patch p, channels c */
 } PkEpilogue;
 
 int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int transA,
                  int transB, const PkEpilogue* epi, void* stream);
+
+/* test hooks: force the GEMM N-tile (64/128/256) or split-K factor; 0 restores the heuristics */
+void pk_gemm_force_bn(int bn);
+void pk_gemm_force_splits(int s);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over channels (nn.LayerNorm(eps=1e-6): models_painter.py:193,200 norm1/norm2, :315,:417 final norm).
+ * x fp32 [M, C] (row stride ldx) -> out (bf16 if out_is_bf16 else fp32; row stride ldo, so it can be a column
+ * slice of the [M, 4C] decoder input, models_painter.py:422); mean/rstd [M] saved for backward (nullable).
+ * bwd: dx = LN'(dy) (+ dres), dgamma/dbeta accumulated atomically (caller zero-initialises).              */
+int pk_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, float eps, void* out,
+                     int ldo, int out_is_bf16, float* mean, float* rstd, int M, int C, void* stream);
+int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* mean, const float* rstd,
+                     const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta, int M,
+                     int C, void* stream);
+
+/* PatchEmbed lowering (util/vitdet_utils.py:178-186, models_painter.py:387-388): rows of (c,r,s)-ordered
+ * patches of imgs then tgts, bf16 [2*B*h*w, Cin*p*p]; the conv itself is pk_gemm_bf16 on these rows.       */
+int pk_im2col_patch(const float* imgs, const float* tgts, void* out_bf16, int B, int Cin, int H, int W, int p,
+                    void* stream);
+
+/* Token assembly (models_painter.py:392-409; SegGPT type tokens models_seggpt.py:414-420) and its backward.
+ * E fp32 [2B*N, C] (x rows then y rows); mask uint8 [maskB, N] (maskB = 1 broadcasts); pos fp32 [N, C];
+ * type_emb fp32 [B, C] or NULL.  bwd: dE bf16 (y rows gated by 1-mask), dpos [N,C], dseg/dmask_token [C]
+ * (atomically accumulated, caller zero-initialises).                                                      */
+int pk_assemble_tokens(const float* E, const uint8_t* mask, int maskB, const float* mask_token,
+                       const float* seg_x, const float* seg_y, const float* pos, const float* type_emb,
+                       float* out, int B, int N, int C, void* stream);
+int pk_assemble_tokens_bwd(const float* dZ, const uint8_t* mask, int maskB, void* dE_bf16, float* dpos,
+                           float* dseg_x, float* dseg_y, float* dmask_token, int B, int N, int C, void* stream);
+
+/* get_abs_pos (util/vitdet_utils.py:141-157): F.interpolate(bicubic, align_corners=False), NHWC [sh,sw,C] ->
+ * [h,w,C]; bwd scatters atomically into a zero-initialised [sh,sw,C].                                      */
+int pk_bicubic_fwd(const float* src, float* dst, int sh, int sw, int h, int w, int C, void* stream);
+int pk_bicubic_bwd(const float* ddst, float* dsrc_accum, int sh, int sw, int h, int w, int C, void* stream);
+
+/* Early merge (models_painter.py:414-415): out = 0.5*(z[:half] + z[half:]); bwd duplicates 0.5*d.          */
+int pk_merge_halves(const float* z, float* out, long long half_elems, void* stream);
+int pk_merge_halves_bwd(const float* d, float* out, long long half_elems, void* stream);
+
+/* fp32 -> bf16 operand casts; optional per-row-group scale (DropPath backward, timm drop_path) and fused
+ * column sums (bias gradients).                                                                           */
+int pk_cast_bf16(const float* in, void* out_bf16, long long n, void* stream);
+int pk_scale_cast_colsum(const float* in, int ldin, const float* rowscale, int rows_per_group, void* out_bf16,
+                         float* colsum, int M, int C, void* stream);
+int pk_colsum_bf16(const void* in_bf16, int ldin, float* colsum, int M, int C, void* stream);
+
+/* Window attention plumbing (util/vitdet_utils.py:16-60 window_partition / window_unpartition; reachable only
+ * through Painter(window_block_indexes=[...]), models_painter.py:220-227): zero-padded bf16 partition of the
+ * [B,H,W,C] token grid into [B*nWh*nWw, ws, ws, C]; inverse: out = (resid or 0) + rowscale[b] * window value.   */
+int pk_window_partition_bf16(const void* in, void* out, int B, int H, int W, int C, int ws, void* stream);
+int pk_window_unpartition(const float* win, const float* resid, const float* rowscale, float* out, int B, int H,
+                          int W, int C, int ws, void* stream);
+
+/* SegGPT multi-prompt feature ensemble + residual (models_seggpt.py:220-231,:233): a, z, out fp32 [G*P, N, C]. */
+int pk_ensemble_resid(const float* a, const float* z, float* out, int G, int P, int N, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention with decomposed relative-position bias (models_painter.py:73-86 + util/vitdet_utils.py:
+ * 63-125).  qkv bf16 [B*h*w, 3*heads*64] with columns (3, head, 64); th/tw = pk_relpos_table_bf16 outputs
+ * (bf16, zero-padded to th_pad/tw_pad rows, multiples of 16); w must divide 112 (2,4,7,8,14,28,56).
+ * fwd: out bf16 [B*N, heads*64], lse fp32 [B*heads, N] (log2 domain, nullable).
+ * bwd: dqkv bf16 like qkv; dTh [2h-1,64], dTw [2w-1,64] fp32 accumulated atomically (zero-initialise);
+ *      scratch: delta [B*heads*N], relh_g [B*heads*N*h], relw_g [B*heads*N*w] fp32.                        */
+int pk_relpos_table_bf16(const float* table, void* out_bf16, int L, int Lpad, void* stream);
+int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void* out, float* lse, int B, int heads, int h,
+                int w, int th_pad, int tw_pad, void* stream);
+int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse, const void* th, const void* tw,
+                void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g, float* relw_g, int B, int heads,
+                int h, int w, int th_pad, int tw_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder head (models_painter.py:328-333,430 decoder_pred = conv3x3 -> LayerNorm2D -> GELU -> conv1x1;
+ * util/vitdet_utils.py:189-209) fused with forward_loss (:433-462) and patchify (:355-368).
+ * g_nhwc: bf16 [B, H, W, 64] (output of the PK_EPI_PIXSHUF GEMM). wmat/wmat_t: pk_conv3x3_pack outputs.
+ * head_params: fp32 [387] = conv3x3 bias[64] | LN2D weight[64] | LN2D bias[64] | conv1x1 weight[3][64] | bias[3].
+ * fwd writes c1 (bf16 conv output, NHWC), patch_out fp32 [B, N, p*p*3] (= patchify(pred)), num[B] += sum
+ * loss*mask*valid.  loss_kind: 0 smoothl1(beta .01), 1 l1, 2 l2, 3 l1l2.
+ * pk_loss_prep: stats[b] = {sum (tgt*std+mean)*(1-M), sum M*valid};  pk_loss_finalize: loss + per-sample
+ * coefficient keep_b/den (the `inds_ign` rule of :446-448; seggpt != 0 selects models_seggpt.py:457-468).      */
+int pk_conv3x3_pack(const float* w, void* wf_bf16, void* wd_bf16, void* stream);
+int pk_loss_prep(const float* tgts, const uint8_t* mask, int maskB, const float* valid, float* stats_zeroed,
+                 int B, int H, int W, int p, void* stream);
+int pk_decoder_head_fwd(const void* g_nhwc, const void* wmat, const float* head_params, const float* tgts,
+                        const uint8_t* mask, int maskB, const float* valid, void* c1_out, float* patch_out,
+                        float* num, int B, int H, int W, int p, int loss_kind, void* stream);
+int pk_loss_finalize(const float* stats, const float* num, float* loss, float* coef, int B, int seggpt,
+                     void* stream);
+int pk_decoder_head_bwd(const void* c1, const float* tgts, const uint8_t* mask, int maskB, const float* valid,
+                        const float* coef, const float* gscale, const float* head_params, void* dc1,
+                        float* dhead_params_zeroed, int B, int H, int W, int p, int loss_kind, void* stream);
+int pk_conv3x3_dgrad_unshuffle(const void* dc1_nhwc, const void* wmat_t, void* out_tok, int B, int H, int W,
+                               int p, void* stream);
+int pk_conv3x3_wgrad(const void* g_nhwc, const void* dc1_nhwc, float* out, int B, int H, int W, void* stream);
+int pk_conv3x3_wgrad_unpack(const float* acc, float* dw, void* stream);
 
 #ifdef __cplusplus
 }

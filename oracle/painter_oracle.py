@@ -107,7 +107,8 @@ def rel_pos_lookup(rel_pos, size):
         t = F.interpolate(rel_pos.t().unsqueeze(0), size=L, mode="linear")[0].t()
     else:
         t = rel_pos
-    idx = torch.arange(size)[:, None] - torch.arange(size)[None, :] + (size - 1)
+    ar = torch.arange(size, device=rel_pos.device)
+    idx = ar[:, None] - ar[None, :] + (size - 1)
     return t[idx]  # [size, size, d]
 
 
@@ -201,10 +202,10 @@ def encoder(imgs, tgts, mask, sd, cfg: PainterConfig, drops=None, seg_type=None,
     x = x + P
     y = y + P
     if cfg.seggpt:
-        te = torch.zeros(B, 1, 1, C, dtype=x.dtype)
+        te = torch.zeros(B, 1, 1, C, dtype=x.dtype, device=x.device)
         st = seg_type.reshape(B)
-        te[st == 0] = sd["type_token_cls"].reshape(1, 1, C)
-        te[st == 1] = sd["type_token_ins"].reshape(1, 1, C)
+        te[st == 0] = sd["type_token_cls"].reshape(1, 1, C).to(te.dtype)
+        te[st == 1] = sd["type_token_ins"].reshape(1, 1, C).to(te.dtype)
         x = x + te
         y = y + te
     z = torch.cat([x, y], 0)
@@ -243,8 +244,8 @@ def loss_fn(pred, tgts, mask, valid, cfg: PainterConfig):
     M = unpatchify(m, p)
     valid = valid.to(pred.dtype)
     if not cfg.seggpt:
-        mean = torch.tensor(IMAGENET_MEAN, dtype=pred.dtype)[None, :, None, None]
-        std = torch.tensor(IMAGENET_STD, dtype=pred.dtype)[None, :, None, None]
+        mean = torch.tensor(IMAGENET_MEAN, dtype=tgts.dtype, device=pred.device)[None, :, None, None]
+        std = torch.tensor(IMAGENET_STD, dtype=tgts.dtype, device=pred.device)[None, :, None, None]
         ign = ((tgts * std + mean) * (1 - M)).sum((1, 2, 3)) < 300
         valid = valid * (~ign).to(pred.dtype)[:, None, None, None]
     Wt = M * valid
@@ -270,7 +271,7 @@ def forward(sd, cfg: PainterConfig, imgs, tgts, bool_masked_pos, valid, drops=No
     (models_painter.py:464-472 / models_seggpt.py:471-479)."""
     h, w = imgs.shape[2] // cfg.patch_size, imgs.shape[3] // cfg.patch_size
     if bool_masked_pos is None:
-        mask = torch.zeros(imgs.shape[0], h * w, dtype=torch.bool)
+        mask = torch.zeros(imgs.shape[0], h * w, dtype=torch.bool, device=imgs.device)
     else:
         mask = bool_masked_pos.flatten(1).to(torch.bool)
     taps = encoder(imgs, tgts, mask, sd, cfg, drops, seg_type, merge_between_batch)

@@ -317,7 +317,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int c = 0; c < 16; ++c) {
           const int kc = c0 + c;
           const float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
-          float p = exp2f(tv - lse);
+          float p = fast_exp2(tv - lse);
           if (kc >= keys_valid || !valid) p = 0.f;
           ds[c] = p * (__uint_as_float(w[c]) - delta);
           gh[kc / W] += ds[c];
@@ -571,7 +571,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int c = 0; c < 16; ++c) {
           const int kc = c0 + c;
           const float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
-          p[c] = exp2f(tv - lse);
+          p[c] = fast_exp2(tv - lse);
           if (kc >= keys_valid || !valid) p[c] = 0.f;
           ds[c] = p[c] * (__uint_as_float(w[c]) - delta) * 0.125f;
         }

@@ -223,30 +223,73 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int keys_valid = (h - j * R) * W;  // >= ATT_KT except in a partial last tile
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      // ---------------- pass 1: row max of t = s*scale + bias (log2 domain) ----------------
-      float mx = -INFINITY;
+      if (j == 0) {
+        // first tile: an explicit max pass fixes the reference point m_ref
+        float mx = -INFINITY;
 #pragma unroll
-      for (int c0 = 0; c0 < ATT_KT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tS + lane_addr + c0, v);
-        tmem_wait_ld();
+        for (int c0 = 0; c0 < ATT_KT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tS + lane_addr + c0, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int kc = c0 + c;
-          float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
-          if (kc >= keys_valid) tv = -INFINITY;
-          mx = fmaxf(mx, tv);
+          for (int c = 0; c < 16; ++c) {
+            const int kc = c0 + c;
+            float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
+            if (kc >= keys_valid) tv = -INFINITY;
+            mx = fmaxf(mx, tv);
+          }
         }
-      }
-      // ---------------- lazy rescale of the running state ----------------
-      const bool grow = mx > m_ref + 8.0f;
-      float alpha = 1.0f;
-      if (grow) {
-        alpha = exp2f(m_ref - mx);  // 0 on the first tile (m_ref = -inf)
-        l_sum *= alpha;
         m_ref = mx;
       }
-      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+      // Optimistic single pass: p = exp2(t - m_ref) with the reference point of the previous tiles while the
+      // tile max is tracked; only if some row's max outgrew m_ref by more than 2^8 is O rescaled and the pass
+      // repeated (rare after the first tiles).  The result is exact for any threshold.
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        float hbm[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) hbm[r] = hb[r] - m_ref;
+        float mx = -INFINITY, l_tile = 0.f;
+        uint32_t v[2][16];
+        tmem_ld_x16(tS + lane_addr, v[0]);
+#pragma unroll
+        for (int ci = 0; ci < ATT_KT / 16; ++ci) {
+          const int c0 = ci * 16;
+          tmem_wait_ld();
+          if (ci + 1 < ATT_KT / 16) tmem_ld_x16(tS + lane_addr + c0 + 16, v[(ci + 1) & 1]);
+          float p[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int kc = c0 + c;
+            float tv = fmaf(__uint_as_float(v[ci & 1][c]), sc, hbm[kc / W] + relw[kc % W]);
+            if (kc >= keys_valid) tv = -INFINITY;
+            mx = fmaxf(mx, tv);
+            p[c] = fast_exp2(tv);
+            l_tile += p[c];
+          }
+          // 16 consecutive keys = two 16-byte chunks of this row inside K-block (c0 / 64)
+          const uint32_t rowbase = sP + (c0 >> 6) * 16384 + row * 128;
+          const int ch = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t addr = rowbase + (((ch + q) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                         "r"(pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1])), "r"(pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3])),
+                         "r"(pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5])), "r"(pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]))
+                         : "memory");
+          }
+        }
+        const bool grow = mx > 8.0f;  // relative to m_ref
+        if (attempt == 1 || !__any_sync(0xffffffffu, grow)) {
+          l_sum += l_tile;
+          break;
+        }
+        // rescale the running state to the new reference point and redo the tile
+        float alpha = 1.0f;
+        if (grow) {
+          alpha = fast_exp2(-mx);
+          m_ref += mx;
+          l_sum *= alpha;
+        }
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 16) {
           uint32_t o[16];
@@ -257,33 +300,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st_x16(tO + lane_addr + c0, o);
         }
         tmem_wait_st();
-      }
-      // ---------------- pass 2: p = exp2(t - m_ref), row sum, bf16 P tile into swizzled smem ----------------
-#pragma unroll
-      for (int c0 = 0; c0 < ATT_KT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tS + lane_addr + c0, v);
-        tmem_wait_ld();
-        float p[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int kc = c0 + c;
-          float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
-          if (kc >= keys_valid) tv = -INFINITY;
-          p[c] = exp2f(tv - m_ref);
-          l_sum += p[c];
-        }
-        // 16 consecutive keys = two 16-byte chunks of this row inside K-block (c0 / 64)
-        const uint32_t rowbase = sP + (c0 >> 6) * 16384 + row * 128;
-        const int ch = (c0 & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint32_t addr = rowbase + (((ch + q) ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1])), "r"(pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3])),
-                       "r"(pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5])), "r"(pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]))
-                       : "memory");
-        }
       }
       fence_proxy_async_smem();
       tc_fence_before();

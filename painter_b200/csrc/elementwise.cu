@@ -598,3 +598,79 @@ extern "C" int pk_ensemble_resid(const float* a, const float* z, float* out, int
   PK_LAUNCH_CHECK("pk_ensemble_resid");
   return 0;
 }
+
+// =============================================================================================
+// Window attention plumbing (vitdet_utils.py:16-60): zero-padded partition of a [B,H,W,C] token grid into
+// [B*nWh*nWw, ws, ws, C] windows and its inverse.  Only reachable through Painter(window_block_indexes=[...]);
+// the stock factories build no windowed block.
+// =============================================================================================
+namespace pk {
+
+// bf16 partition: 16-byte chunks (8 channels)
+__global__ void window_partition_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H,
+                                             int W, int C8, int ws, int nWh, int nWw) {
+  const size_t total = static_cast<size_t>(B) * nWh * nWw * ws * ws * C8;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    size_t r = idx / C8;
+    const int wx = static_cast<int>(r % ws); r /= ws;
+    const int wy = static_cast<int>(r % ws); r /= ws;
+    const int ww = static_cast<int>(r % nWw); r /= nWw;
+    const int wh = static_cast<int>(r % nWh);
+    const int b = static_cast<int>(r / nWh);
+    const int y = wh * ws + wy, x = ww * ws + wx;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y < H && x < W) v = in[((static_cast<size_t>(b) * H + y) * W + x) * C8 + c];
+    out[idx] = v;
+  }
+}
+
+// out[b,y,x,:] = (resid ? resid[b,y,x,:] : 0) + scale_b * win[window(b,y,x), :]   (fp32, float4 chunks)
+__global__ void window_unpartition_kernel(const float4* __restrict__ win, const float4* __restrict__ resid,
+                                          const float* __restrict__ rowscale, float4* __restrict__ out, int B,
+                                          int H, int W, int C4, int ws, int nWh, int nWw) {
+  const size_t total = static_cast<size_t>(B) * H * W * C4;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C4);
+    size_t r = idx / C4;
+    const int x = static_cast<int>(r % W); r /= W;
+    const int y = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    const size_t widx =
+        ((((static_cast<size_t>(b) * nWh + y / ws) * nWw + x / ws) * ws + y % ws) * ws + x % ws) * C4 + c;
+    const float sc = rowscale ? rowscale[b] : 1.f;
+    float4 v = win[widx];
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    if (resid) {
+      const float4 rr = resid[idx];
+      v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+    }
+    out[idx] = v;
+  }
+}
+}  // namespace pk
+
+extern "C" int pk_window_partition_bf16(const void* in, void* out, int B, int H, int W, int C, int ws,
+                                        void* stream) {
+  PK_CHECK(in && out && C % 8 == 0 && ws > 0, "pk_window_partition_bf16: bad args");
+  const int nWh = (H + ws - 1) / ws, nWw = (W + ws - 1) / ws;
+  const size_t total = static_cast<size_t>(B) * nWh * nWw * ws * ws * (C / 8);
+  pk::window_partition_bf16_kernel<<<pk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8, ws, nWh, nWw);
+  PK_LAUNCH_CHECK("pk_window_partition_bf16");
+  return 0;
+}
+
+extern "C" int pk_window_unpartition(const float* win, const float* resid, const float* rowscale, float* out,
+                                     int B, int H, int W, int C, int ws, void* stream) {
+  PK_CHECK(win && out && C % 4 == 0 && ws > 0, "pk_window_unpartition: bad args");
+  const int nWh = (H + ws - 1) / ws, nWw = (W + ws - 1) / ws;
+  const size_t total = static_cast<size_t>(B) * H * W * (C / 4);
+  pk::window_unpartition_kernel<<<pk::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(win), reinterpret_cast<const float4*>(resid), rowscale,
+      reinterpret_cast<float4*>(out), B, H, W, C / 4, ws, nWh, nWw);
+  PK_LAUNCH_CHECK("pk_window_unpartition");
+  return 0;
+}

@@ -149,103 +149,118 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
   }
 }
 
-// One 32-column chunk of one output row.
-__device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, int row, int col,
+// Generic epilogue for one 32-row x 32-column accumulator chunk of one epilogue warp.
+// Phase 1 (thread = accumulator row): alpha, bias, per-sample row scale -> private smem staging tile.
+// Phase 2 (lane = 4 consecutive columns, 8 lanes per row, 4 rows per instruction): every global access of the
+// warp covers whole contiguous row segments (128 B fp32 / 64 B bf16) instead of 32 scattered rows.
+constexpr int STG_LD = 36;  // floats per staged row: 16-byte aligned, conflict-free for float4 quarter-warps
+
+__device__ __forceinline__ uint2 pack4_bf16(const float4& v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  return u;
+}
+__device__ __forceinline__ float4 unpack4_bf16(const uint2& u) {
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xFFFF0000u));
+}
+
+__device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* stg, int row0, int M, int col,
                                                     const uint32_t (&v)[32]) {
-  float x[32];
-  const float alpha = e.alpha;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * alpha;
-  if (e.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b = __ldg(b4 + q);
-      x[q * 4 + 0] += b.x;
-      x[q * 4 + 1] += b.y;
-      x[q * 4 + 2] += b.z;
-      x[q * 4 + 3] += b.w;
-    }
-  }
-  const size_t off = static_cast<size_t>(row) * e.ldc + col;
-  switch (e.kind) {
-    case PK_EPI_BF16: {
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(e.out) + off, x);
-    } break;
-    case PK_EPI_F32: {
-      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
-      if (e.accumulate == 2) {  // split-K partials
-        float* df = reinterpret_cast<float*>(d);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(df + j, x[j]);
-      } else if (e.accumulate) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = d[q];
-          o.x += x[q * 4 + 0];
-          o.y += x[q * 4 + 1];
-          o.z += x[q * 4 + 2];
-          o.w += x[q * 4 + 3];
-          d[q] = o;
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          d[q] = make_float4(x[q * 4 + 0], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
-      }
-    } break;
-    case PK_EPI_GELU: {
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(e.out) + off, x);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = gelu_erf(bf16_round(x[j]));
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(e.out2) + off, x);
-    } break;
-    case PK_EPI_RESID: {
-      const float sc = e.rowscale ? __ldg(e.rowscale + row / e.rows_per_group) : 1.0f;
-      const float4* r4 = reinterpret_cast<const float4*>(
-          reinterpret_cast<const float*>(e.aux) + static_cast<size_t>(row) * e.ld_aux + col);
-      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
+  const int lane = threadIdx.x & 31;
+  {
+    // ---- phase 1 ----
+    const int row = row0 + lane;
+    float sc = e.alpha;
+    if (e.kind == PK_EPI_RESID && e.rowscale != nullptr && row < M) sc *= __ldg(e.rowscale + row / e.rows_per_group);
+    float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
+    if (e.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+      const float bsc = e.kind == PK_EPI_RESID ? sc / e.alpha : 1.0f;  // rowscale also multiplies the bias
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 r = r4[q];
-        d[q] = make_float4(fmaf(sc, x[q * 4 + 0], r.x), fmaf(sc, x[q * 4 + 1], r.y),
-                           fmaf(sc, x[q * 4 + 2], r.z), fmaf(sc, x[q * 4 + 3], r.w));
+        const float4 b = __ldg(b4 + q);
+        srow[q] = make_float4(fmaf(__uint_as_float(v[q * 4 + 0]), sc, b.x * bsc),
+                              fmaf(__uint_as_float(v[q * 4 + 1]), sc, b.y * bsc),
+                              fmaf(__uint_as_float(v[q * 4 + 2]), sc, b.z * bsc),
+                              fmaf(__uint_as_float(v[q * 4 + 3]), sc, b.w * bsc));
       }
-    } break;
-    case PK_EPI_DGELU: {
-      const uint4* z4 = reinterpret_cast<const uint4*>(
-          reinterpret_cast<const __nv_bfloat16*>(e.aux) + static_cast<size_t>(row) * e.ld_aux + col);
+    } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 z = z4[q];
-        const uint32_t w[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float z0 = __uint_as_float(w[t] << 16);
-          const float z1 = __uint_as_float(w[t] & 0xFFFF0000u);
-          x[q * 8 + t * 2 + 0] *= gelu_erf_grad(z0);
-          x[q * 8 + t * 2 + 1] *= gelu_erf_grad(z1);
-        }
-      }
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(e.out) + off, x);
-    } break;
-    case PK_EPI_PIXSHUF: {
-      const int hw = e.ps_h * e.ps_w;
-      const int b = row / hw, t = row - b * hw;
-      const int i = t / e.ps_w, j = t - i * e.ps_w;
-      const int pc = e.ps_p * e.ps_c;
-      const int r = col / pc, rem = col - r * pc;
-      const int s = rem / e.ps_c, c = rem - s * e.ps_c;
-      const size_t o = ((static_cast<size_t>(b) * (e.ps_h * e.ps_p) + i * e.ps_p + r) *
-                            (static_cast<size_t>(e.ps_w) * e.ps_p) +
-                        j * e.ps_p + s) *
-                           e.ps_c +
-                       c;
-      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(e.out) + o, x);
-    } break;
-    default:
-      break;
+      for (int q = 0; q < 8; ++q)
+        srow[q] = make_float4(__uint_as_float(v[q * 4 + 0]) * sc, __uint_as_float(v[q * 4 + 1]) * sc,
+                              __uint_as_float(v[q * 4 + 2]) * sc, __uint_as_float(v[q * 4 + 3]) * sc);
+    }
   }
+  __syncwarp();
+  // ---- phase 2 ----
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    const int row = row0 + r;
+    if (row >= M) continue;
+    float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
+    const int cc = col + c4;
+    const size_t off = static_cast<size_t>(row) * e.ldc + cc;
+    switch (e.kind) {
+      case PK_EPI_BF16:
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(x);
+        break;
+      case PK_EPI_F32: {
+        float* d = reinterpret_cast<float*>(e.out) + off;
+        if (e.accumulate == 2) {  // split-K partials
+          atomicAdd(d + 0, x.x);
+          atomicAdd(d + 1, x.y);
+          atomicAdd(d + 2, x.z);
+          atomicAdd(d + 3, x.w);
+        } else {
+          if (e.accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(d);
+            x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+          }
+          *reinterpret_cast<float4*>(d) = x;
+        }
+      } break;
+      case PK_EPI_GELU: {
+        const uint2 zb = pack4_bf16(x);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = zb;
+        const float4 zr = unpack4_bf16(zb);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + off) =
+            pack4_bf16(make_float4(gelu_erf(zr.x), gelu_erf(zr.y), gelu_erf(zr.z), gelu_erf(zr.w)));
+      } break;
+      case PK_EPI_RESID: {
+        const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.aux) +
+                                                           static_cast<size_t>(row) * e.ld_aux + cc);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) =
+            make_float4(x.x + rr.x, x.y + rr.y, x.z + rr.z, x.w + rr.w);
+      } break;
+      case PK_EPI_DGELU: {
+        const float4 z = unpack4_bf16(*reinterpret_cast<const uint2*>(
+            reinterpret_cast<const __nv_bfloat16*>(e.aux) + static_cast<size_t>(row) * e.ld_aux + cc));
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(make_float4(
+            x.x * gelu_erf_grad(z.x), x.y * gelu_erf_grad(z.y), x.z * gelu_erf_grad(z.z), x.w * gelu_erf_grad(z.w)));
+      } break;
+      case PK_EPI_PIXSHUF: {
+        const int hw = e.ps_h * e.ps_w;
+        const int b = row / hw, t = row - b * hw;
+        const int i = t / e.ps_w, j = t - i * e.ps_w;
+        const int pc = e.ps_p * e.ps_c;
+        const int rr = cc / pc, rem = cc - rr * pc;
+        const int ss = rem / e.ps_c, c = rem - ss * e.ps_c;
+        const size_t o = ((static_cast<size_t>(b) * (e.ps_h * e.ps_p) + i * e.ps_p + rr) *
+                              (static_cast<size_t>(e.ps_w) * e.ps_p) +
+                          j * e.ps_p + ss) *
+                             e.ps_c +
+                         c;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + o) = pack4_bf16(x);
+      } break;
+      default:
+        break;
+    }
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -270,6 +285,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t holder = bar_base + 8u * (2 * stages + 4);
   volatile uint32_t* holder_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (holder - base));
+  float* stg_gen = reinterpret_cast<float*>(smem_gen + (bar_base - base) + 256);  // 4 x [32][STG_LD] fp32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -432,11 +448,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
+        float* stg = stg_gen + ew * (32 * STG_LD);
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld_x32(taddr + c0, v);
           tmem_wait_ld();
-          if (row < g.M) gemm_epilogue_chunk(g.epi, row, n_blk * BN + c0, v);
+          gemm_epilogue_chunk(g.epi, stg, m_blk * GEMM_BM + ew * 32, g.M, n_blk * BN + c0, v);
         }
       }
       tc_fence_before();
@@ -456,7 +473,8 @@ int g_force_splits = 0;
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs& g, cudaStream_t st,
                        const char* who) {
-  const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + g.BN * 128) + 256;
+  const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + g.BN * 128) + 256 +
+                      4 * 32 * STG_LD * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =

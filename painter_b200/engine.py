@@ -16,15 +16,12 @@ from .ops import EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_PIXSHUF, EPI_RESID
 
 LOSS_KINDS = {"smoothl1": 0, "l1": 1, "l2": 2, "l1l2": 3}
 
-_bf16_cache = {}
-
-
 def bf16_weight(p, shape2d=None):
-    """bf16 copy of an fp32 parameter, cached on (storage, version): recast only after an optimizer step."""
-    key = id(p)
-    ent = _bf16_cache.get(key)
+    """bf16 copy of an fp32 parameter, cached ON the parameter object and keyed by (version, storage): the cast is
+    redone only after an optimizer step / load_state_dict changed the values."""
+    ent = getattr(p, "_pk_bf16", None)
     ver = p._version
-    if ent is not None and ent[0] == ver and ent[1] == p.data_ptr():
+    if ent is not None and ent[0] == ver and ent[1] == p.data_ptr() and ent[2].device == p.device:
         return ent[2]
     src = p.detach()
     if not src.is_contiguous():
@@ -32,7 +29,7 @@ def bf16_weight(p, shape2d=None):
     w = ops.cast_bf16(src)
     if shape2d is not None:
         w = w.view(shape2d)
-    _bf16_cache[key] = (ver, p.data_ptr(), w)
+    p._pk_bf16 = (ver, p.data_ptr(), w)
     return w
 
 

@@ -328,3 +328,23 @@ def conv3x3_wgrad(g_nhwc, dc1):
     dw = torch.empty((64, 64, 3, 3), dtype=torch.float32, device=dc1.device)
     check(lib().pk_conv3x3_wgrad_unpack(_ptr(acc), _ptr(dw), _stream()), "pk_conv3x3_wgrad_unpack")
     return dw
+
+
+def window_partition_bf16(x, B, H, W, ws):
+    """bf16 [B*H*W, C] -> zero-padded windows [B*nWh*nWw*ws*ws, C]."""
+    _req(x, torch.bfloat16, "x")
+    C = x.shape[1]
+    nWh, nWw = (H + ws - 1) // ws, (W + ws - 1) // ws
+    out = torch.empty((B * nWh * nWw * ws * ws, C), dtype=torch.bfloat16, device=x.device)
+    check(lib().pk_window_partition_bf16(_ptr(x), _ptr(out), B, H, W, C, ws, _stream()), "pk_window_partition_bf16")
+    return out
+
+
+def window_unpartition(win, B, H, W, ws, resid=None, rowscale=None):
+    """fp32 windows -> fp32 [B*H*W, C] (+ resid, per-sample scale)."""
+    _req(win, torch.float32, "win")
+    C = win.shape[1]
+    out = torch.empty((B * H * W, C), dtype=torch.float32, device=win.device)
+    check(lib().pk_window_unpartition(_ptr(win), _ptr(resid), _ptr(rowscale), _ptr(out), B, H, W, C, ws, _stream()),
+          "pk_window_unpartition")
+    return out

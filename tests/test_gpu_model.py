@@ -20,13 +20,29 @@ def _to(dev, *ts):
     return [t.to(dev) for t in ts]
 
 
-def _check_grads(model, ref_grads, ref_norms=None):
+def _reference_bf16_noise(cfg, sd, imgs, tgts, mask, valid, drops=None):
+    """Error of the reference algorithm ITSELF when run under torch.autocast('cuda', bf16) (the oracle restatement
+    uses the same torch ops, so CUDA autocast gives it the reference's dtype flow) against its fp32 result.
+    SURVEY.md section 8(c): ours must stay within 1.5x of this noise floor."""
+    sdc = {k: v.cuda().requires_grad_(True) for k, v in sd.items()}
+    args = [t.cuda() for t in (imgs, tgts, mask, valid)]
+    d = None if drops is None else [tuple(t.cuda() for t in pair) for pair in drops]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss, pred, _ = po.forward(sdc, cfg, *args, drops=d)
+    loss.float().backward()
+    return {k: v.grad for k, v in sdc.items()}, pred.float()
+
+
+def _check_grads(model, ref_grads, ref_norms=None, noise=None):
     named = dict(model.named_parameters())
     bad = []
     for k, g in ref_grads.items():
         e = rel_rms(named[k].grad, g)
-        if e > GRAD_RMS:
-            bad.append((k, e))
+        tol = GRAD_RMS
+        if noise is not None:
+            tol = max(tol, 1.5 * rel_rms(noise[k], g))
+        if e > tol:
+            bad.append((k, e, tol))
     if ref_norms is not None:
         for k, n in ref_norms.items():
             gn = named[k].grad.float().norm().item()
@@ -47,7 +63,9 @@ def test_painter_tiny_eval_fwd_bwd_vs_reference_golden():
     assert rel_rms(pred, ev["pred"]) <= LOGIT_RMS and rel_max(pred, ev["pred"]) <= LOGIT_MAX
     assert torch.equal(m.cpu(), ev["mask"])
     loss.backward()
-    _check_grads(model, ev["grads"], ev["grad_norms"])
+    noise, npred = _reference_bf16_noise(cfg, synth_state_dict(cfg, gold["weight_seed"]), imgs, tgts, mask, valid)
+    print("pred rms-rel ours", rel_rms(pred, ev["pred"]), "reference-bf16", rel_rms(npred, ev["pred"]))
+    _check_grads(model, ev["grads"], ev["grad_norms"], noise)
 
 
 def test_painter_tiny_train_mode_droppath_replay():
@@ -58,14 +76,14 @@ def test_painter_tiny_train_mode_droppath_replay():
     imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, **gold["inputs"]))
     torch.manual_seed(gold["train_seed"])
     drops = po.draw_drop_scales(cfg, imgs.shape[0])  # the reference's CPU draws, replayed
-    it = iter(drops)
     model._drop_scales = lambda i, Bp, dev: tuple(t.to(dev) for t in drops[i])
     loss, pred, _ = model(imgs, tgts, mask, valid)
     tr = gold["train"]
     assert abs(loss.item() - tr["loss"].item()) <= LOSS_TOL * abs(tr["loss"].item())
     assert rel_rms(pred, tr["pred"]) <= LOGIT_RMS
     loss.backward()
-    _check_grads(model, tr["grads"], tr["grad_norms"])
+    noise, _ = _reference_bf16_noise(cfg, synth_state_dict(cfg, gold["weight_seed"]), imgs, tgts, mask, valid, drops)
+    _check_grads(model, tr["grads"], tr["grad_norms"], noise)
 
 
 def test_painter_tiny_interpolated_tables():
@@ -108,7 +126,7 @@ def test_full_size_forward_vs_oracle():
     imgs, tgts, mask, valid = synth_inputs(cfg, 1, 21)
     with torch.no_grad():
         loss, pred, _ = model(imgs.cuda(), tgts.cuda(), mask.cuda(), valid.cuda())
-        torch.set_num_threads(max(1, torch.get_num_threads()))
+        torch.set_num_threads(min(32, torch.get_num_threads()))  # 100+ threads oversubscribe the CPU oracle
         rl, rp, _ = po.forward(sd, cfg, imgs, tgts, mask, valid)
     assert abs(loss.item() - rl.item()) <= LOSS_TOL * abs(rl.item())
     assert rel_rms(pred, rp) <= LOGIT_RMS and rel_max(pred, rp) <= LOGIT_MAX

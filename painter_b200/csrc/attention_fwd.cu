@@ -39,7 +39,15 @@ struct AttnFwdArgs {
   __nv_bfloat16* out;     // [B*N, ldo]
   int ldo;
   float* lse;             // [B*heads, N]  (log2 domain: m + log2(l))
+  long long* trace;       // optional debug timeline (CTA 0 only): [role][tile][event] clock64 stamps
 };
+
+// debug timeline: role 0 = producer, 1 = MMA issuer, 2 = softmax row 0; 8 events per tile
+#define ATT_TRACE(role, tile, ev)                                                                     \
+  do {                                                                                                \
+    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 16)   \
+      a.trace[((role) * 16 + (tile)) * 8 + (ev)] = clock64();                                          \
+  } while (0)
 
 template <int W>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -106,9 +114,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_3d(sV, &tmKV, bar_vf, 2 * C + head * 64, 0, b);
       for (int j = 1; j < num_tiles; ++j) {
         mbar_wait(bar_ke, (j - 1) & 1);
+        ATT_TRACE(0, j, 0);
         mbar_expect_tx(bar_kf, ATT_KT * 128);
         tma_load_3d(sK, &tmKV, bar_kf, C + head * 64, j * ATT_KT, b);
         mbar_wait(bar_ve, (j - 1) & 1);
+        ATT_TRACE(0, j, 1);
         mbar_expect_tx(bar_vf, ATT_KT * 128);
         tma_load_3d(sV, &tmKV, bar_vf, 2 * C + head * 64, j * ATT_KT, b);
       }
@@ -139,15 +149,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_qk = make_idesc_bf16(128, ATT_KT, false, false);
       const uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
       for (int j = 0; j < num_tiles; ++j) {
+        ATT_TRACE(1, j, 0);
         mbar_wait(bar_kf, j & 1);
+        ATT_TRACE(1, j, 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sK + k * 32, 16, 1024), idesc_qk, k != 0);
         umma_commit(bar_ke);
         umma_commit(bar_s);
+        ATT_TRACE(1, j, 2);
         mbar_wait(bar_p, j & 1);
+        ATT_TRACE(1, j, 3);
         mbar_wait(bar_vf, j & 1);
+        ATT_TRACE(1, j, 4);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < ATT_KT / 16; ++kk)
@@ -221,7 +236,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         hb[r] = my_relh[i < h ? i : h - 1];
       }
       const int keys_valid = (h - j * R) * W;  // >= ATT_KT except in a partial last tile
+      if (row == 0) ATT_TRACE(2, j, 0);
       mbar_wait(bar_s, j & 1);
+      if (row == 0) ATT_TRACE(2, j, 1);
       tc_fence_after();
       if (j == 0) {
         // first tile: an explicit max pass fixes the reference point m_ref
@@ -301,9 +318,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tmem_wait_st();
       }
+      if (row == 0) ATT_TRACE(2, j, 2);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
+      if (row == 0) ATT_TRACE(2, j, 3);
     }
     // ---------------- epilogue: O / l -> bf16, LSE ----------------
     mbar_wait(bar_o, 0);
@@ -341,6 +360,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 using namespace pk;
 
+static long long* g_attn_trace = nullptr;
+// debug hook: device buffer of 3*16*8 int64 receiving a clock64 timeline of CTA (0,0,0); nullptr disables
+extern "C" void pk_attn_set_trace(void* buf) { g_attn_trace = static_cast<long long*>(buf); }
+
 // qkv: bf16 [B*N, 3C] (columns (3, head, 64) as produced by the qkv Linear, models_painter.py:76-78)
 // th / tw: bf16 rel-pos tables, zero-padded to th_pad / tw_pad rows (multiples of 16), [rows, 64]
 extern "C" int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void* out, float* lse, int B,
@@ -365,6 +388,7 @@ extern "C" int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void
   a.out = static_cast<__nv_bfloat16*>(out);
   a.ldo = C;
   a.lse = lse;
+  a.trace = g_attn_trace;
 
   CUtensorMap tmQ, tmKV, tmTh, tmTw;
   {

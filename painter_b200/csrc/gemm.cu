@@ -166,6 +166,7 @@ __device__ __forceinline__ float4 unpack4_bf16(const uint2& u) {
                      __uint_as_float(u.y & 0xFFFF0000u));
 }
 
+template <int KIND>
 __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* stg, int row0, int M, int col,
                                                     const uint32_t (&v)[32]) {
   const int lane = threadIdx.x & 31;
@@ -173,11 +174,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
     // ---- phase 1 ----
     const int row = row0 + lane;
     float sc = e.alpha;
-    if (e.kind == PK_EPI_RESID && e.rowscale != nullptr && row < M) sc *= __ldg(e.rowscale + row / e.rows_per_group);
+    if (KIND == PK_EPI_RESID && e.rowscale != nullptr && row < M) sc *= __ldg(e.rowscale + row / e.rows_per_group);
     float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
     if (e.bias != nullptr) {
       const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
-      const float bsc = e.kind == PK_EPI_RESID ? sc / e.alpha : 1.0f;  // rowscale also multiplies the bias
+      const float bsc = KIND == PK_EPI_RESID ? sc / e.alpha : 1.0f;  // rowscale also multiplies the bias
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 b = __ldg(b4 + q);
@@ -196,73 +197,65 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
   __syncwarp();
   // ---- phase 2 ----
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  const int cc = col + c4;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rsub;
     const int row = row0 + r;
     if (row >= M) continue;
     float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
-    const int cc = col + c4;
     const size_t off = static_cast<size_t>(row) * e.ldc + cc;
-    switch (e.kind) {
-      case PK_EPI_BF16:
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(x);
-        break;
-      case PK_EPI_F32: {
-        float* d = reinterpret_cast<float*>(e.out) + off;
-        if (e.accumulate == 2) {  // split-K partials
-          atomicAdd(d + 0, x.x);
-          atomicAdd(d + 1, x.y);
-          atomicAdd(d + 2, x.z);
-          atomicAdd(d + 3, x.w);
-        } else {
-          if (e.accumulate) {
-            const float4 o = *reinterpret_cast<const float4*>(d);
-            x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
-          }
-          *reinterpret_cast<float4*>(d) = x;
+    if constexpr (KIND == PK_EPI_BF16) {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(x);
+    } else if constexpr (KIND == PK_EPI_F32) {
+      float* d = reinterpret_cast<float*>(e.out) + off;
+      if (e.accumulate == 2) {  // split-K partials
+        atomicAdd(d + 0, x.x);
+        atomicAdd(d + 1, x.y);
+        atomicAdd(d + 2, x.z);
+        atomicAdd(d + 3, x.w);
+      } else {
+        if (e.accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(d);
+          x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
         }
-      } break;
-      case PK_EPI_GELU: {
-        const uint2 zb = pack4_bf16(x);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = zb;
-        const float4 zr = unpack4_bf16(zb);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + off) =
-            pack4_bf16(make_float4(gelu_erf(zr.x), gelu_erf(zr.y), gelu_erf(zr.z), gelu_erf(zr.w)));
-      } break;
-      case PK_EPI_RESID: {
-        const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.aux) +
-                                                           static_cast<size_t>(row) * e.ld_aux + cc);
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) =
-            make_float4(x.x + rr.x, x.y + rr.y, x.z + rr.z, x.w + rr.w);
-      } break;
-      case PK_EPI_DGELU: {
-        const float4 z = unpack4_bf16(*reinterpret_cast<const uint2*>(
-            reinterpret_cast<const __nv_bfloat16*>(e.aux) + static_cast<size_t>(row) * e.ld_aux + cc));
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(make_float4(
-            x.x * gelu_erf_grad(z.x), x.y * gelu_erf_grad(z.y), x.z * gelu_erf_grad(z.z), x.w * gelu_erf_grad(z.w)));
-      } break;
-      case PK_EPI_PIXSHUF: {
-        const int hw = e.ps_h * e.ps_w;
-        const int b = row / hw, t = row - b * hw;
-        const int i = t / e.ps_w, j = t - i * e.ps_w;
-        const int pc = e.ps_p * e.ps_c;
-        const int rr = cc / pc, rem = cc - rr * pc;
-        const int ss = rem / e.ps_c, c = rem - ss * e.ps_c;
-        const size_t o = ((static_cast<size_t>(b) * (e.ps_h * e.ps_p) + i * e.ps_p + rr) *
-                              (static_cast<size_t>(e.ps_w) * e.ps_p) +
-                          j * e.ps_p + ss) *
-                             e.ps_c +
-                         c;
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + o) = pack4_bf16(x);
-      } break;
-      default:
-        break;
+        *reinterpret_cast<float4*>(d) = x;
+      }
+    } else if constexpr (KIND == PK_EPI_GELU) {
+      const uint2 zb = pack4_bf16(x);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = zb;
+      const float4 zr = unpack4_bf16(zb);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + off) =
+          pack4_bf16(make_float4(gelu_erf(zr.x), gelu_erf(zr.y), gelu_erf(zr.z), gelu_erf(zr.w)));
+    } else if constexpr (KIND == PK_EPI_RESID) {
+      const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.aux) +
+                                                         static_cast<size_t>(row) * e.ld_aux + cc);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) =
+          make_float4(x.x + rr.x, x.y + rr.y, x.z + rr.z, x.w + rr.w);
+    } else if constexpr (KIND == PK_EPI_DGELU) {
+      const float4 z = unpack4_bf16(*reinterpret_cast<const uint2*>(
+          reinterpret_cast<const __nv_bfloat16*>(e.aux) + static_cast<size_t>(row) * e.ld_aux + cc));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(make_float4(
+          x.x * gelu_erf_grad(z.x), x.y * gelu_erf_grad(z.y), x.z * gelu_erf_grad(z.z), x.w * gelu_erf_grad(z.w)));
+    } else if constexpr (KIND == PK_EPI_PIXSHUF) {
+      const int hw = e.ps_h * e.ps_w;
+      const int b = row / hw, t = row - b * hw;
+      const int i = t / e.ps_w, j = t - i * e.ps_w;
+      const int pc = e.ps_p * e.ps_c;
+      const int rr = cc / pc, rem = cc - rr * pc;
+      const int ss = rem / e.ps_c, c = rem - ss * e.ps_c;
+      const size_t o = ((static_cast<size_t>(b) * (e.ps_h * e.ps_p) + i * e.ps_p + rr) *
+                            (static_cast<size_t>(e.ps_w) * e.ps_p) +
+                        j * e.ps_p + ss) *
+                           e.ps_c +
+                       c;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + o) = pack4_bf16(x);
     }
   }
   __syncwarp();
 }
 
+template <int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmArgs g) {
@@ -416,12 +409,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rloc = ew * 32 + lane;
       const int row = m_blk * GEMM_BM + rloc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      if (g.conv.mode == 1) {
+      if constexpr (KIND == EPI_HEAD || KIND == EPI_UNSHUF) {
         // pixel-row tile: rloc -> (b, y, x)
         const int tx = m_blk % g.conv.tiles_x, r1 = m_blk / g.conv.tiles_x;
         const int ty = r1 % g.conv.tiles_y, bi = r1 / g.conv.tiles_y;
         const int y = ty * g.conv.TH + rloc / g.conv.TW, x = tx * g.conv.TW + rloc % g.conv.TW;
-        if (g.epi.kind == EPI_HEAD) {
+        if constexpr (KIND == EPI_HEAD) {
           float c[64];
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -453,7 +446,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld_x32(taddr + c0, v);
           tmem_wait_ld();
-          gemm_epilogue_chunk(g.epi, stg, m_blk * GEMM_BM + ew * 32, g.M, n_blk * BN + c0, v);
+          gemm_epilogue_chunk<KIND>(g.epi, stg, m_blk * GEMM_BM + ew * 32, g.M, n_blk * BN + c0, v);
         }
       }
       tc_fence_before();
@@ -475,17 +468,33 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs&
                        const char* who) {
   const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + g.BN * 128) + 256 +
                       4 * 32 * STG_LD * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    PK_CHECK(e == cudaSuccess, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
-    attr_set = true;
-  }
   const int total = g.num_m_tiles * g.num_n_tiles * g.splits;
   const int sms = sm_count();
   const int grid = total < sms ? total : sms;
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g);
+#define PK_GEMM_CASE(KK)                                                                                       \
+  case KK: {                                                                                                   \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           227 * 1024);                                                        \
+      PK_CHECK(e == cudaSuccess, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));                  \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    gemm_bf16_kernel<KK><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g);                                       \
+  } break;
+  switch (g.epi.kind) {
+    PK_GEMM_CASE(PK_EPI_BF16)
+    PK_GEMM_CASE(PK_EPI_F32)
+    PK_GEMM_CASE(PK_EPI_GELU)
+    PK_GEMM_CASE(PK_EPI_RESID)
+    PK_GEMM_CASE(PK_EPI_DGELU)
+    PK_GEMM_CASE(PK_EPI_PIXSHUF)
+    PK_GEMM_CASE(EPI_HEAD)
+    PK_GEMM_CASE(EPI_UNSHUF)
+    default:
+      PK_CHECK(false, "%s: bad epilogue kind %d", who, g.epi.kind);
+  }
+#undef PK_GEMM_CASE
   PK_LAUNCH_CHECK(who);
   return 0;
 }

@@ -89,22 +89,35 @@ class EmbedFn(torch.autograd.Function):
 
 
 class BlockFn(torch.autograd.Function):
-    """x [B'*N, C] fp32 -> same.  meta = (Bp, h, w, heads, eps, ens_groups, ens_P)."""
+    """x [B'*N, C] fp32 -> same.  meta = (Bp, h, w, heads, eps, ens_groups, ens_P, ws); ws > 0 = windowed block
+    (vitdet_utils.window_partition / window_unpartition around the attention, models_painter.py:220-227)."""
 
     @staticmethod
     def forward(ctx, x, drop_a, drop_m, n1w, n1b, rel_h, rel_w, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w,
                 fc1_b, fc2_w, fc2_b, meta):
-        Bp, h, w, heads, eps, ens_groups, ens_P = meta
+        Bp, h, w, heads, eps, ens_groups, ens_P, ws = meta
         N = h * w
         M, C = x.shape
         u, mean1, rstd1 = ops.layernorm_fwd(x, n1w, n1b, eps)
         wqkv, wproj = bf16_weight(qkv_w), bf16_weight(proj_w)
         wfc1, wfc2 = bf16_weight(fc1_w), bf16_weight(fc2_w)
-        qkv = ops.gemm(u, wqkv, kind=EPI_BF16, bias=qkv_b)
         th = ops.relpos_table_bf16(rel_h.contiguous())
         tw = ops.relpos_table_bf16(rel_w.contiguous())
-        ao, lse = ops.attn_fwd(qkv, th, tw, Bp, heads, h, w)
-        if ens_groups > 0:
+        if ws > 0:
+            if ens_groups > 0:
+                raise NotImplementedError("painter_b200: prompt ensemble inside a windowed block")
+            u = ops.window_partition_bf16(u, Bp, h, w, ws)   # zero-padded windows [Bp*nW*ws*ws, C]
+            Bw = u.shape[0] // (ws * ws)
+            qkv = ops.gemm(u, wqkv, kind=EPI_BF16, bias=qkv_b)
+            ao, lse = ops.attn_fwd(qkv, th, tw, Bw, heads, ws, ws)
+            a = ops.gemm(ao, wproj, kind=EPI_F32, bias=proj_b)
+            x1 = ops.window_unpartition(a, Bp, h, w, ws, resid=x, rowscale=drop_a)
+        else:
+            qkv = ops.gemm(u, wqkv, kind=EPI_BF16, bias=qkv_b)
+            ao, lse = ops.attn_fwd(qkv, th, tw, Bp, heads, h, w)
+        if ws > 0:
+            pass
+        elif ens_groups > 0:
             a = ops.gemm(ao, wproj, kind=EPI_F32, bias=proj_b)
             x1 = ops.ensemble_resid(a, x, ens_groups, ens_P, N, C)
         else:
@@ -121,7 +134,7 @@ class BlockFn(torch.autograd.Function):
     def backward(ctx, dx2):
         (x, mean1, rstd1, u, qkv, ao, lse, th, tw, x1, mean2, rstd2, v, z, hact, wqkv, wproj, wfc1, wfc2, n1w, n2w,
          drop_a, drop_m) = ctx.saved_tensors
-        Bp, h, w, heads, eps, ens_groups, ens_P = ctx.meta
+        Bp, h, w, heads, eps, ens_groups, ens_P, ws = ctx.meta
         if ens_groups > 0:
             raise NotImplementedError("painter_b200: backward through the SegGPT prompt ensemble is not implemented")
         N = h * w
@@ -140,12 +153,20 @@ class BlockFn(torch.autograd.Function):
         dx1 = ops.layernorm_bwd(dv, x1, mean2, rstd2, n2w, dn2w, dn2b, dres=dx2)
         # ---- attention branch ----
         da, dproj_b = ops.scale_cast_colsum(dx1, drop_a, N)
+        if ws > 0:
+            da = ops.window_partition_bf16(da, Bp, h, w, ws)
+            Bw = da.shape[0] // (ws * ws)
         dproj_w = _wgrad(da, ao)
         dao = ops.gemm(da, wproj, trans_b=True, kind=EPI_BF16)
-        dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bp, heads, h, w)
+        if ws > 0:
+            dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bw, heads, ws, ws)
+        else:
+            dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bp, heads, h, w)
         dqkv_b = ops.colsum_bf16(dqkv)
         dqkv_w = _wgrad(dqkv, u)
         du = ops.gemm(dqkv, wqkv, trans_b=True, kind=EPI_F32)
+        if ws > 0:
+            du = ops.window_unpartition(du, Bp, h, w, ws)   # gradients at padded tokens are dropped
         dn1w = torch.zeros(C, dtype=torch.float32, device=dev)
         dn1b = torch.zeros(C, dtype=torch.float32, device=dev)
         dx = ops.layernorm_bwd(du, x, mean1, rstd1, n1w, dn1w, dn1b, dres=dx1)

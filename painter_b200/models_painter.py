@@ -234,19 +234,19 @@ class Painter(nn.Module):
         Bp = 2 * B
         taps = []
         for i, blk in enumerate(self.blocks):
-            if blk.window_size > 0:
-                raise NotImplementedError("painter_b200: windowed blocks are not implemented yet (the stock factories "
-                                          "build none, SURVEY.md section 0.1)")
+            ws = blk.window_size
+            if ws > 0 and 112 % ws != 0:
+                raise NotImplementedError(f"painter_b200: window_size {ws} unsupported (must divide 112: 2,4,7,8,14,28)")
             ens_g, ens_p = 0, 0
             if merge_between_batch >= 0 and i >= merge_between_batch:
                 ens_g, ens_p = (2, B) if merge_idx >= i else (1, B)
             da, dm = self._drop_scales(i, Bp, dev)
             a = blk.attn
-            rel_h = engine.resize_rel_table(a.rel_pos_h, h)
-            rel_w = engine.resize_rel_table(a.rel_pos_w, w)
+            rel_h = engine.resize_rel_table(a.rel_pos_h, ws if ws > 0 else h)
+            rel_w = engine.resize_rel_table(a.rel_pos_w, ws if ws > 0 else w)
             prm = blk.params()
             z = BlockFn.apply(z, da, dm, prm[0], prm[1], rel_h, rel_w, *prm[4:],
-                              (Bp, h, w, self.num_heads, blk.norm1.eps, ens_g, ens_p))
+                              (Bp, h, w, self.num_heads, blk.norm1.eps, ens_g, ens_p, ws))
             if i == merge_idx:
                 z = MergeFn.apply(z)
                 Bp = B

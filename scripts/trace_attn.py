@@ -1,0 +1,28 @@
+"""Timeline of one attention-forward CTA (clock64 stamps) — debug aid."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from painter_b200 import ops, _lib
+B, heads, h, w = 8, 16, 56, 28
+N, C = h * w, heads * 64
+qkv = torch.randn(B * N, 3 * C, device="cuda").bfloat16()
+th = ops.relpos_table_bf16(torch.randn(2 * h - 1, 64, device="cuda") * 0.1)
+tw = ops.relpos_table_bf16(torch.randn(2 * w - 1, 64, device="cuda") * 0.1)
+for _ in range(3):
+    ops.attn_fwd(qkv, th, tw, B, heads, h, w)
+buf = torch.zeros(3 * 16 * 8, dtype=torch.int64, device="cuda")
+_lib.lib().pk_attn_set_trace(ctypes.c_void_p(buf.data_ptr()))
+ops.attn_fwd(qkv, th, tw, B, heads, h, w)
+torch.cuda.synchronize()
+_lib.lib().pk_attn_set_trace(None)
+t = buf.cpu().view(3, 16, 8)
+t0 = int(t[1, 0, 0])
+names = {0: ["ke_seen", "ve_seen"], 1: ["loop_top", "kf_seen", "qk_issued", "p_seen", "vf_seen"],
+         2: ["before_wait_s", "s_seen", "softmax_done", "arrived_p"]}
+for j in range(14):
+    line = f"tile {j:2d}: "
+    for role in (1, 2, 0):
+        for e, nm in enumerate(names[role]):
+            v = int(t[role, j, e])
+            line += f"{'PMS'[role] if False else ['prod','mma','smx'][role]}.{nm}={v - t0 if v else -1:7d} "
+    print(line)

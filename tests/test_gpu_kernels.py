@@ -25,7 +25,7 @@ def _seed():
 @pytest.mark.parametrize("bn", [0, 64, 128, 256])
 def test_gemm_operand_majors_and_tiles(ta, tb, bn):
     from painter_b200 import _lib, ops
-    M, N, K = 300, 512, 200
+    M, N, K = 304, 512, 200
     a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
     b = (torch.randn(N, K, device=DEV) * 0.5).bfloat16()
     bias = torch.randn(N, device=DEV)
@@ -186,6 +186,24 @@ def test_merge_cast_colsum_ensemble():
     ref = a.clone().view(G, P, N, C)
     ref[:, :, N // 2:] = ref[:, :, N // 2:].mean(1, keepdim=True)
     assert relmax(got, zz + ref.view(G * P, N, C)) < 1e-6
+
+
+def test_window_partition_roundtrip_matches_reference_semantics():
+    from painter_b200 import ops
+    B, H, W, C, ws = 2, 8, 4, 128, 7
+    x = torch.randn(B * H * W, C, device=DEV).bfloat16()
+    win = ops.window_partition_bf16(x, B, H, W, ws)
+    xp = F.pad(x.view(B, H, W, C), (0, 0, 0, (ws - W % ws) % ws, 0, (ws - H % ws) % ws))
+    Hp, Wp = xp.shape[1], xp.shape[2]
+    ref = xp.view(B, Hp // ws, ws, Wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, C)   # vitdet_utils.py:35-36
+    assert torch.equal(win, ref)
+    a = torch.randn(win.shape[0], C, device=DEV)
+    res = torch.randn(B * H * W, C, device=DEV)
+    rs = torch.tensor([0.0, 1.25], device=DEV)
+    out = ops.window_unpartition(a, B, H, W, ws, resid=res, rowscale=rs)
+    back = a.view(B, Hp // ws, Wp // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)[:, :H, :W]
+    want = res.view(B, H, W, C) + rs.view(B, 1, 1, 1) * back
+    assert relmax(out.view(B, H, W, C), want) < 1e-6
 
 
 # ---------------------------------------------------------------- attention -----------------------------------

@@ -100,6 +100,23 @@ def test_painter_tiny_interpolated_tables():
     assert rel_rms(pred, it["pred"]) <= LOGIT_RMS
 
 
+def test_painter_tiny_window_blocks_vs_reference_golden():
+    """Real windowed blocks (non-stock, parameterised): ws=7 on the 8x4 grid pads to 14x7 (vitdet_utils.py:29-33)."""
+    gold = load_golden("painter_tiny_window.pt")
+    cfg = po.PainterConfig(**gold["cfg"])
+    model, _ = build_model(cfg, gold["weight_seed"])
+    model.eval()
+    assert sorted({b.window_size for b in model.blocks}) == [0, 7]
+    imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, **gold["inputs"]))
+    loss, pred, _ = model(imgs, tgts, mask, valid)
+    ev = gold["eval"]
+    assert abs(loss.item() - ev["loss"].item()) <= LOSS_TOL * abs(ev["loss"].item())
+    assert rel_rms(pred, ev["pred"]) <= LOGIT_RMS
+    loss.backward()
+    noise, _ = _reference_bf16_noise(cfg, synth_state_dict(cfg, gold["weight_seed"]), imgs, tgts, mask, valid)
+    _check_grads(model, ev["grads"], ev["grad_norms"], noise)
+
+
 def test_seggpt_tiny_prompts_and_ensemble():
     gold = load_golden("seggpt_tiny.pt")
     cfg = po.PainterConfig(**gold["cfg"])

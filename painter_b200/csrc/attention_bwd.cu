@@ -22,7 +22,8 @@ namespace pk {
 
 constexpr int AB_BM = 128;
 constexpr int AB_KT = 112;
-constexpr int AB_THREADS = 192;
+constexpr int AB_THREADS = 320;   // TMA warp + MMA warp + 8 softmax warps
+constexpr int AB_SMX = 256;       // softmax threads
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -98,11 +99,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_ke, 1);
     mbar_init(bar_ke + 8, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, AB_SMX);
     mbar_init(bar_g, 1);
-    mbar_init(bar_gr, 128);
+    mbar_init(bar_gr, AB_SMX);
     mbar_init(bar_e, 1);
-    mbar_init(bar_er, 128);
+    mbar_init(bar_er, AB_SMX);
     mbar_init(bar_t, 1);
     fence_barrier_init();
   }
@@ -210,7 +211,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
+    // 8 warps: warps 2..5 own key columns [0,56) of every tile, warps 6..9 columns [56,112); the two warps with
+    // the same (warp & 3) share the 32 TMEM lanes (= query rows) of that quarter.
+    constexpr int RH = R / 2;  // image rows per half tile (56 % W == 0 for every supported W)
+    static_assert(RH * 2 == R && (AB_KT / 2) % W == 0, "tile halves must be whole image rows");
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cbase = half * (AB_KT / 2);
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     int t = q0 + row;
@@ -239,12 +246,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     const float lse = a.lse[bh * a.N + t];
-    if (valid) a.delta[bh * a.N + t] = delta;
+    if (valid && half == 0) a.delta[bh * a.N + t] = delta;
 
     // ---- rel_w -> registers (+ global for kernel B) ----
     float relw[W];
     {
-      float* scratch = relh_gen + static_cast<size_t>(row) * 17;
+      float* scratch = relh_gen + (static_cast<size_t>(half) * 128 + row) * 17;
       mbar_wait(bar_g, 0);
       tc_fence_after();
       for (int c0 = 0; c0 < a.tw_pad; c0 += 16) {
@@ -262,30 +269,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       mbar_arrive(bar_gr);
-      if (valid) {
+      if (valid && half == 0) {
         float* dst = a.relw_g + (bh * a.N + t) * W;
 #pragma unroll
         for (int j = 0; j < W; ++j) dst[j] = relw[j];
       }
     }
-    // ---- rel_h -> smem (+ global) ; zero the Gh' row ----
+    // ---- rel_h -> smem (+ global): written by half 0, read by both halves after the first bar_s ----
     {
       mbar_wait(bar_g, 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < a.th_pad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tS + lane_addr + c0, v);
-        tmem_wait_ld();
+      if (half == 0) {
+        for (int c0 = 0; c0 < a.th_pad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tS + lane_addr + c0, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int i = i_r + (h - 1) - (c0 + c);
-          if (i >= 0 && i < h) my_relh[i] = __uint_as_float(v[c]) * AB_LOG2E;
+          for (int c = 0; c < 16; ++c) {
+            const int i = i_r + (h - 1) - (c0 + c);
+            if (i >= 0 && i < h) my_relh[i] = __uint_as_float(v[c]) * AB_LOG2E;
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       mbar_arrive(bar_gr);
-      if (valid) {
+      if (valid && half == 0) {
         float* dst = a.relh_g + (bh * a.N + t) * h;
         for (int i = 0; i < h; ++i) dst[i] = my_relh[i];
       }
@@ -296,45 +305,63 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int j = 0; j < W; ++j) gw[j] = 0.f;
     const float sc = a.scale_log2;
     for (int j = 0; j < num_tiles; ++j) {
-      float hb[R], gh[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = j * R + r;
-        hb[r] = my_relh[i < h ? i : h - 1];
-        gh[r] = 0.f;
-      }
-      const int keys_valid = (h - j * R) * W;
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
+      float hb[RH], gh[RH];
 #pragma unroll
-      for (int c0 = 0; c0 < AB_KT; c0 += 16) {
+      for (int r = 0; r < RH; ++r) {
+        const int i = j * R + half * RH + r;
+        hb[r] = my_relh[i < h ? i : h - 1] - lse;
+        gh[r] = 0.f;
+      }
+      const int keys_valid = (h - j * R) * W - cbase;  // columns of this half that are real keys
+      const bool full = keys_valid >= AB_KT / 2 && valid;
+      const uint32_t tS_h = tS + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
+      // 56 columns per thread: 16 + 16 + 16 + 8
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ci * 16;
+        const int nc = ci < 3 ? 16 : 8;
         uint32_t v[16], w[16];
-        tmem_ld_x16(tS + lane_addr + c0, v);
-        tmem_ld_x16(tdP + lane_addr + c0, w);
+        if (ci < 3) {
+          tmem_ld_x16(tS_h + c0, v);
+          tmem_ld_x16(tdP_h + c0, w);
+        } else {
+          uint32_t v8[8], w8[8];
+          tmem_ld_x8(tS_h + c0, v8);
+          tmem_ld_x8(tdP_h + c0, w8);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            v[c] = v8[c];
+            w[c] = w8[c];
+          }
+        }
         tmem_wait_ld();
         float ds[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const int kc = c0 + c;
-          const float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
-          float p = fast_exp2(tv - lse);
-          if (kc >= keys_valid || !valid) p = 0.f;
-          ds[c] = p * (__uint_as_float(w[c]) - delta);
-          gh[kc / W] += ds[c];
-          gw[kc % W] += ds[c];
-          ds[c] *= 0.125f;
+          if (c < nc) {
+            const int kc = c0 + c;
+            float p = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]));
+            if (!full && (kc >= keys_valid || !valid)) p = 0.f;
+            ds[c] = p * (__uint_as_float(w[c]) - delta);
+            gh[kc / W] += ds[c];
+            gw[kc % W] += ds[c];
+          }
         }
-        const uint32_t rowbase = sdS + (c0 >> 6) * 16384 + row * 128;
-        const int ch = (c0 & 63) >> 3;
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-          st_shared_v4(rowbase + (((ch + q) ^ (row & 7)) << 4), pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
-                       pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]), pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]),
-                       pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+        for (int q = 0; q < 2; ++q) {
+          if (q * 8 < nc) {
+            const int g8 = ((cbase + c0) >> 3) + q;  // 8-column group inside the 112-wide tile
+            st_shared_v4(sdS + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4),
+                         pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]), pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]),
+                         pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]), pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+          }
+        }
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = j * R + r;
+      for (int r = 0; r < RH; ++r) {
+        const int i = j * R + half * RH + r;
         if (i < h) my_gh[i] = gh[r];
       }
       fence_proxy_async_smem();
@@ -342,15 +369,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(bar_p);
     }
 
-    // ---------------- epilogue phase 1: Gh^ (bf16, K-major / MN-major dual view) ----------------
+    // ---------------- epilogue phase 1: Gh^ x 8 (bf16, K-major / MN-major dual view) ----------------
+    // (dS is stored unscaled, so the accumulator holds 8 * dQ_bias + dS.K; the final read-out multiplies by 1/8)
     mbar_wait(bar_e, 0);
     tc_fence_after();
-    for (int c0 = 0; c0 < a.th_pad; c0 += 8) {
+    for (int c0 = half * 8; c0 < a.th_pad; c0 += 16) {
       float g[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int i = i_r + (h - 1) - (c0 + c);
-        g[c] = (i >= 0 && i < h) ? my_gh[i] : 0.f;
+        g[c] = (i >= 0 && i < h) ? my_gh[i] * 8.0f : 0.f;
       }
       const uint32_t addr = sdS + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
       st_shared_v4(addr, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
@@ -359,69 +387,81 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_er);
-    // ---------------- epilogue phase 2: dT_h atomics, then Gw^ ----------------
+    // ---------------- epilogue phase 2: dT_h atomics, then Gw^ x 8 ----------------
     mbar_wait(bar_e, 1);
     tc_fence_after();
     for (int mh = 0; mh * 128 < a.th_pad; ++mh) {
       const int tt = mh * 128 + row;
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < 32; c0 += 16) {
         uint32_t v[16];
-        tmem_ld_x16(tS + lane_addr + mh * 64 + c0, v);
+        tmem_ld_x16(tS + lane_addr + mh * 64 + half * 32 + c0, v);
         tmem_wait_ld();
         if (tt < 2 * h - 1) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) atomicAdd(a.dTh + tt * 64 + c0 + c, __uint_as_float(v[c]));
+          for (int c = 0; c < 16; ++c)
+            atomicAdd(a.dTh + tt * 64 + half * 32 + c0 + c, __uint_as_float(v[c]) * 0.125f);
         }
       }
     }
     {
-      // zero this row of the first two K-blocks, then scatter gw[j] to column t = j_r + W-1 - j
-      const uint32_t rb0 = sdS + row * 128, rb1 = sdS + 16384 + row * 128;
+      // combine the two halves' column sums through smem (the rel_h / Gh' rows are dead by now)
+      float* xch = relh_gen + static_cast<size_t>(row) * (W + 1);
+      if (half == 1) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        st_shared_v4(rb0 + (q << 4), 0u, 0u, 0u, 0u);
-        st_shared_v4(rb1 + (q << 4), 0u, 0u, 0u, 0u);
+        for (int j = 0; j < W; ++j) xch[j] = gw[j];
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(AB_SMX) : "memory");
+      if (half == 0) {
+        // zero this row of the first two K-blocks, then scatter gw[j] to column t = j_r + W-1 - j
+        const uint32_t rb0 = sdS + row * 128, rb1 = sdS + 16384 + row * 128;
 #pragma unroll
-      for (int j = 0; j < W; ++j) {
-        const int tt = j_r + (W - 1) - j;
-        const uint32_t addr = sdS + (tt >> 6) * 16384 + row * 128 + ((((tt & 63) >> 3) ^ (row & 7)) << 4) +
-                              (tt & 7) * 2;
-        const __nv_bfloat16 bv = __float2bfloat16_rn(gw[j]);
-        asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&bv)) : "memory");
+        for (int q = 0; q < 8; ++q) {
+          st_shared_v4(rb0 + (q << 4), 0u, 0u, 0u, 0u);
+          st_shared_v4(rb1 + (q << 4), 0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const int tt = j_r + (W - 1) - j;
+          const uint32_t addr = sdS + (tt >> 6) * 16384 + row * 128 + ((((tt & 63) >> 3) ^ (row & 7)) << 4) +
+                                (tt & 7) * 2;
+          const __nv_bfloat16 bv = __float2bfloat16_rn((gw[j] + xch[j]) * 8.0f);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&bv))
+                       : "memory");
+        }
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_er);
-    // ---------------- epilogue phase 3: dT_w atomics, dQ -> bf16 ----------------
+    // ---------------- epilogue phase 3: dT_w atomics, dQ -> bf16 (each half owns 32 of the 64 columns) -----------
     mbar_wait(bar_e, 0);
     tc_fence_after();
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
+    for (int c0 = 0; c0 < 32; c0 += 16) {
       uint32_t v[16];
-      tmem_ld_x16(tS + lane_addr + c0, v);
+      tmem_ld_x16(tS + lane_addr + half * 32 + c0, v);
       tmem_wait_ld();
       if (row < 2 * W - 1) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) atomicAdd(a.dTw + row * 64 + c0 + c, __uint_as_float(v[c]));
+        for (int c = 0; c < 16; ++c)
+          atomicAdd(a.dTw + row * 64 + half * 32 + c0 + c, __uint_as_float(v[c]) * 0.125f);
       }
     }
-    __nv_bfloat16* qrow = a.dqkv + (static_cast<size_t>(b) * a.N + t) * (3 * C) + head * 64;
+    __nv_bfloat16* qrow = a.dqkv + (static_cast<size_t>(b) * a.N + t) * (3 * C) + head * 64 + half * 32;
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
+    for (int c0 = 0; c0 < 32; c0 += 16) {
       uint32_t o[16];
-      tmem_ld_x16(tdQ + lane_addr + c0, o);
+      tmem_ld_x16(tdQ + lane_addr + half * 32 + c0, o);
       tmem_wait_ld();
       if (valid) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]), __uint_as_float(o[q * 8 + 1]));
-          u.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3]));
-          u.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5]));
-          u.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7]));
+          u.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * 0.125f, __uint_as_float(o[q * 8 + 1]) * 0.125f);
+          u.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * 0.125f, __uint_as_float(o[q * 8 + 3]) * 0.125f);
+          u.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * 0.125f, __uint_as_float(o[q * 8 + 5]) * 0.125f);
+          u.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * 0.125f, __uint_as_float(o[q * 8 + 7]) * 0.125f);
           *reinterpret_cast<uint4*>(qrow + c0 + q * 8) = u;
         }
       }
@@ -477,7 +517,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(bar_qe, 1);
     mbar_init(bar_qe + 8, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, AB_SMX);
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
@@ -534,88 +574,108 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       umma_commit(bar_o);
     }
   } else {
+    // 8 softmax warps, same column split as kernel A
+    constexpr int RH = R / 2;
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cbase = half * (AB_KT / 2);
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const size_t bh = static_cast<size_t>(b) * a.heads + head;
     const float sc = a.scale_log2;
-    const int keys_valid = (h - jt * R) * W;
+    const int keys_valid = (h - jt * R) * W - cbase;
     for (int i = 0; i < num_q; ++i) {
       int t = i * AB_BM + row;
       const bool valid = t < a.N;
       if (!valid) t = a.N - 1;
       const float lse = a.lse[bh * a.N + t];
       const float delta = a.delta[bh * a.N + t];
-      float hb[R], relw[W];
+      float hb[RH], relw[W];
       {
         const float* ph = a.relh_g + (bh * a.N + t) * h;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int ii = jt * R + r;
-          hb[r] = ph[ii < h ? ii : h - 1];
+        for (int r = 0; r < RH; ++r) {
+          const int ii = jt * R + half * RH + r;
+          hb[r] = ph[ii < h ? ii : h - 1] - lse;
         }
         const float* pw = a.relw_g + (bh * a.N + t) * W;
 #pragma unroll
         for (int j = 0; j < W; ++j) relw[j] = pw[j];
       }
+      const bool full = keys_valid >= AB_KT / 2 && valid;
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
+      const uint32_t tS_h = tS + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
 #pragma unroll
-      for (int c0 = 0; c0 < AB_KT; c0 += 16) {
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ci * 16;
+        const int nc = ci < 3 ? 16 : 8;
         uint32_t v[16], w[16];
-        tmem_ld_x16(tS + lane_addr + c0, v);
-        tmem_ld_x16(tdP + lane_addr + c0, w);
+        if (ci < 3) {
+          tmem_ld_x16(tS_h + c0, v);
+          tmem_ld_x16(tdP_h + c0, w);
+        } else {
+          uint32_t v8[8], w8[8];
+          tmem_ld_x8(tS_h + c0, v8);
+          tmem_ld_x8(tdP_h + c0, w8);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            v[c] = v8[c];
+            w[c] = w8[c];
+          }
+        }
         tmem_wait_ld();
         float p[16], ds[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const int kc = c0 + c;
-          const float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
-          p[c] = fast_exp2(tv - lse);
-          if (kc >= keys_valid || !valid) p[c] = 0.f;
-          ds[c] = p[c] * (__uint_as_float(w[c]) - delta) * 0.125f;
+          if (c < nc) {
+            const int kc = c0 + c;
+            p[c] = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]));
+            if (!full && (kc >= keys_valid || !valid)) p[c] = 0.f;
+            ds[c] = p[c] * (__uint_as_float(w[c]) - delta);
+          }
         }
-        const uint32_t off = (c0 >> 6) * 16384 + row * 128;
-        const int ch = (c0 & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const uint32_t sw = (((ch + q) ^ (row & 7)) << 4);
-          st_shared_v4(sP + off + sw, pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]), pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]),
-                       pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5]), pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]));
-          st_shared_v4(sdS + off + sw, pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
-                       pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]), pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]),
-                       pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+          if (q * 8 < nc) {
+            const int g8 = ((cbase + c0) >> 3) + q;
+            const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
+            st_shared_v4(sP + off, pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]), pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]),
+                         pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5]), pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]));
+            st_shared_v4(sdS + off, pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
+                         pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]), pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]),
+                         pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+          }
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
     }
-    // epilogue: accumulator row = key (jt*112 + row), rows >= 112 are padding
+    // epilogue: accumulator row = key (jt*112 + row), rows >= 112 are padding; half 0 writes dK (x 1/8: dS is
+    // stored unscaled), half 1 writes dV
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const int u = jt * AB_KT + row;
     const bool kvalid = row < AB_KT && u < a.N;
-    __nv_bfloat16* krow = a.dqkv + (static_cast<size_t>(b) * a.N + (kvalid ? u : 0)) * (3 * C) + C + head * 64;
+    __nv_bfloat16* dst = a.dqkv + (static_cast<size_t>(b) * a.N + (kvalid ? u : 0)) * (3 * C) + C + head * 64 +
+                         half * C;
+    const uint32_t tacc = half == 0 ? tdK : tdV;
+    const float osc = half == 0 ? 0.125f : 1.0f;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t tacc = which == 0 ? tdK : tdV;
-      __nv_bfloat16* dst = krow + which * C;
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld_x16(tacc + lane_addr + c0, o);
+      tmem_wait_ld();
+      if (kvalid) {
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t o[16];
-        tmem_ld_x16(tacc + lane_addr + c0, o);
-        tmem_wait_ld();
-        if (kvalid) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint4 uu;
-            uu.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]), __uint_as_float(o[q * 8 + 1]));
-            uu.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3]));
-            uu.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5]));
-            uu.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c0 + q * 8) = uu;
-          }
+        for (int q = 0; q < 2; ++q) {
+          uint4 uu;
+          uu.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * osc, __uint_as_float(o[q * 8 + 1]) * osc);
+          uu.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * osc, __uint_as_float(o[q * 8 + 3]) * osc);
+          uu.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * osc, __uint_as_float(o[q * 8 + 5]) * osc);
+          uu.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * osc, __uint_as_float(o[q * 8 + 7]) * osc);
+          *reinterpret_cast<uint4*>(dst + c0 + q * 8) = uu;
         }
       }
     }
@@ -646,7 +706,8 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   AttnBwdArgs a;
   a.h = h; a.N = N; a.heads = heads; a.th_pad = th_pad; a.tw_pad = tw_pad;
   int relh_bytes = 128 * (h + 1) * 4;
-  if (relh_bytes < 20480) relh_bytes = 20480;
+  if (relh_bytes < 20480) relh_bytes = 20480;                        // 256 x 17 fp32 scratch rows (rel_w gather)
+  if (relh_bytes < 128 * (w + 1) * 4) relh_bytes = 128 * (w + 1) * 4;  // Gw' exchange between the column halves
   relh_bytes = (relh_bytes + 15) & ~15;
   a.relh_bytes = relh_bytes;
   a.scale_log2 = 0.125f * AB_LOG2E;

@@ -261,6 +261,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // Optimistic single pass: p = exp2(t - m_ref) with the reference point of the previous tiles while the
       // tile max is tracked; only if some row's max outgrew m_ref by more than 2^8 is O rescaled and the pass
       // repeated (rare after the first tiles).  The result is exact for any threshold.
+      const bool full = keys_valid >= ATT_KT;
       for (int attempt = 0; attempt < 2; ++attempt) {
         float hbm[R];
 #pragma unroll
@@ -278,7 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < 16; ++c) {
             const int kc = c0 + c;
             float tv = fmaf(__uint_as_float(v[ci & 1][c]), sc, hbm[kc / W] + relw[kc % W]);
-            if (kc >= keys_valid) tv = -INFINITY;
+            if (!full && kc >= keys_valid) tv = -INFINITY;
             mx = fmaxf(mx, tv);
             p[c] = fast_exp2(tv);
             l_tile += p[c];

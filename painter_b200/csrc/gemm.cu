@@ -170,8 +170,40 @@ template <int KIND>
 __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* stg, int row0, int M, int col,
                                                     const uint32_t (&v)[32]) {
   const int lane = threadIdx.x & 31;
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  const int cc = col + c4;
+  // ---- phase 0: issue every global read of phase 2 up front (one exposed latency per chunk, not eight) ----
+  float4 auxf[8];
+  uint2 auxh[8];
+  if constexpr (KIND == PK_EPI_RESID) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + rsub;
+      auxf[it] = row < M ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.aux) +
+                                                            static_cast<size_t>(row) * e.ld_aux + cc)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if constexpr (KIND == PK_EPI_DGELU) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + rsub;
+      auxh[it] = row < M ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) +
+                                                           static_cast<size_t>(row) * e.ld_aux + cc)
+                         : make_uint2(0u, 0u);
+    }
+  } else if constexpr (KIND == PK_EPI_F32) {
+    if (e.accumulate == 1) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = row0 + it * 4 + rsub;
+        auxf[it] = row < M ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) +
+                                                              static_cast<size_t>(row) * e.ldc + cc)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
   {
-    // ---- phase 1 ----
+    // ---- phase 1 (thread = accumulator row) ----
     const int row = row0 + lane;
     float sc = e.alpha;
     if (KIND == PK_EPI_RESID && e.rowscale != nullptr && row < M) sc *= __ldg(e.rowscale + row / e.rows_per_group);
@@ -195,15 +227,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
     }
   }
   __syncwarp();
-  // ---- phase 2 ----
-  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-  const int cc = col + c4;
+  // ---- phase 2 (lane = 4 consecutive columns; 8 lanes per row, 4 rows per instruction) ----
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rsub;
     const int row = row0 + r;
-    if (row >= M) continue;
     float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
+    if (row >= M) continue;
     const size_t off = static_cast<size_t>(row) * e.ldc + cc;
     if constexpr (KIND == PK_EPI_BF16) {
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(x);
@@ -215,9 +245,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
         atomicAdd(d + 2, x.z);
         atomicAdd(d + 3, x.w);
       } else {
-        if (e.accumulate) {
-          const float4 o = *reinterpret_cast<const float4*>(d);
-          x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+        if (e.accumulate == 1) {
+          x.x += auxf[it].x; x.y += auxf[it].y; x.z += auxf[it].z; x.w += auxf[it].w;
         }
         *reinterpret_cast<float4*>(d) = x;
       }
@@ -228,13 +257,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + off) =
           pack4_bf16(make_float4(gelu_erf(zr.x), gelu_erf(zr.y), gelu_erf(zr.z), gelu_erf(zr.w)));
     } else if constexpr (KIND == PK_EPI_RESID) {
-      const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.aux) +
-                                                         static_cast<size_t>(row) * e.ld_aux + cc);
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) =
-          make_float4(x.x + rr.x, x.y + rr.y, x.z + rr.z, x.w + rr.w);
+          make_float4(x.x + auxf[it].x, x.y + auxf[it].y, x.z + auxf[it].z, x.w + auxf[it].w);
     } else if constexpr (KIND == PK_EPI_DGELU) {
-      const float4 z = unpack4_bf16(*reinterpret_cast<const uint2*>(
-          reinterpret_cast<const __nv_bfloat16*>(e.aux) + static_cast<size_t>(row) * e.ld_aux + cc));
+      const float4 z = unpack4_bf16(auxh[it]);
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(make_float4(
           x.x * gelu_erf_grad(z.x), x.y * gelu_erf_grad(z.y), x.z * gelu_erf_grad(z.z), x.w * gelu_erf_grad(z.w)));
     } else if constexpr (KIND == PK_EPI_PIXSHUF) {

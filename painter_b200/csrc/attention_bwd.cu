@@ -58,7 +58,15 @@ struct AttnBwdArgs {
   __nv_bfloat16* dqkv;       // [B*N, 3C]
   float* dTh;                // [2h-1, 64] fp32 atomics
   float* dTw;                // [2W-1, 64]
+  long long* trace;          // optional debug timeline of CTA (0,0,0): [kernel][role][iter][event]
 };
+
+#define AB_TRACE(kern, role, it, ev)                                                                       \
+  do {                                                                                                     \
+    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 16 &&         \
+        ((role) == 1 || (threadIdx.x & 31) == 0))                                                           \
+      a.trace[(((kern) * 2 + (role)) * 16 + (it)) * 8 + (ev)] = clock64();                                   \
+  } while (0)
 
 template <int W>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -99,7 +107,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_ke, 1);
     mbar_init(bar_ke + 8, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, AB_SMX);
+    mbar_init(bar_p, AB_SMX / 32);
     mbar_init(bar_g, 1);
     mbar_init(bar_gr, AB_SMX);
     mbar_init(bar_e, 1);
@@ -137,77 +145,103 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(sTw, &tmTw, bar_t, 0, 0);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // -------------------------------------- MMA issuer --------------------------------------
+      // warp-uniform control flow; the tcgen05 instructions themselves are issued by one elected lane
       mbar_wait(bar_q, 0);
       tc_fence_after();
       {  // G_w = Q . T_w^T
         const uint32_t idesc = make_idesc_bf16(128, a.tw_pad, false, false);
         const uint32_t sT = sKV + 28672 + 14336;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sT + k * 32, 16, 1024), idesc, k != 0);
-        umma_commit(bar_g);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sT + k * 32, 16, 1024), idesc, k != 0);
+          umma_commit(bar_g);
+        }
+        __syncwarp();
       }
       mbar_wait(bar_gr, 0);
       tc_fence_after();
       {  // G_h = Q . T_h^T
         const uint32_t idesc = make_idesc_bf16(128, a.th_pad, false, false);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sdS + k * 32, 16, 1024), idesc, k != 0);
-        umma_commit(bar_g);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sdS + k * 32, 16, 1024), idesc, k != 0);
+          umma_commit(bar_g);
+        }
+        __syncwarp();
       }
       mbar_wait(bar_gr, 1);
       tc_fence_after();
       const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
       const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
+      const uint64_t dQ0 = make_sdesc(sQ, 16, 1024), ddO0 = make_sdesc(sdO, 16, 1024);
+      const uint64_t ddS0 = make_sdesc(sdS, 16, 1024);
       for (int j = 0; j < num_tiles; ++j) {
         const int st = j & 1;
         const uint32_t sK = sKV + st * 28672, sV = sK + 14336;
+        const uint64_t dK0 = make_sdesc(sK, 16, 1024), dV0 = make_sdesc(sV, 16, 1024);
+        AB_TRACE(0, 0, j, 0);
         mbar_wait(bar_kf + 8 * st, (j >> 1) & 1);
+        AB_TRACE(0, 0, j, 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sK + k * 32, 16, 1024), idesc_s, k != 0);
+          for (int k = 0; k < 4; ++k) umma_ss(tS, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tdP, make_sdesc(sdO + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc_s, k != 0);
-        umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k) umma_ss(tdP, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
+        AB_TRACE(0, 0, j, 2);
         mbar_wait(bar_p, j & 1);
+        AB_TRACE(0, 0, j, 3);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < AB_KT / 16; ++kk)
-          umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                  make_sdesc(sK + kk * 2048, 16, 1024), idesc_dq, (j | kk) != 0);
-        umma_commit(bar_ke + 8 * st);
+          for (int kk = 0; kk < AB_KT / 16; ++kk)
+            umma_ss(tdQ, sdesc_add(ddS0, (kk >> 2) * 16384 + (kk & 3) * 32), sdesc_add(dK0, kk * 2048), idesc_dq,
+                    (j | kk) != 0);
+          umma_commit(bar_ke + 8 * st);
+        }
+        __syncwarp();
+        AB_TRACE(0, 0, j, 4);
       }
-      umma_commit(bar_e);  // completion #1 (parity 0): main loop retired
+      if (elect_one()) umma_commit(bar_e);  // completion #1 (parity 0): main loop retired
+      __syncwarp();
       // ---- epilogue phase 1: dQ += Gh^ . T_h ; dT_h = Gh^^T . Q ----
       const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
       mbar_wait(bar_er, 0);
       mbar_wait(bar_t, 0);
       tc_fence_after();
-      for (int kk = 0; kk < a.th_pad / 16; ++kk)
-        umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                make_sdesc(sTh + kk * 2048, 16, 1024), idesc_dq, 1u);
-      for (int mh = 0; mh * 128 < a.th_pad; ++mh)
+      if (elect_one()) {
+        for (int kk = 0; kk < a.th_pad / 16; ++kk)
+          umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                  make_sdesc(sTh + kk * 2048, 16, 1024), idesc_dq, 1u);
+        for (int mh = 0; mh * 128 < a.th_pad; ++mh)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tS + mh * 64, make_sdesc(sdS + (2 * mh) * 16384 + kk * 2048, 16384, 1024),
-                  make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt, kk != 0);
-      umma_commit(bar_e);  // completion #2 (parity 1)
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tS + mh * 64, make_sdesc(sdS + (2 * mh) * 16384 + kk * 2048, 16384, 1024),
+                    make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt, kk != 0);
+        umma_commit(bar_e);  // completion #2 (parity 1)
+      }
+      __syncwarp();
       // ---- epilogue phase 2: dQ += Gw^ . T_w ; dT_w = Gw^^T . Q ----
       mbar_wait(bar_er, 1);
       tc_fence_after();
-      for (int kk = 0; kk < a.tw_pad / 16; ++kk)
-        umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                make_sdesc(sTw + kk * 2048, 16, 1024), idesc_dq, 1u);
+      if (elect_one()) {
+        for (int kk = 0; kk < a.tw_pad / 16; ++kk)
+          umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                  make_sdesc(sTw + kk * 2048, 16, 1024), idesc_dq, 1u);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma_ss(tS, make_sdesc(sdS + kk * 2048, 16384, 1024), make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt,
-                kk != 0);
-      umma_commit(bar_e);  // completion #3 (parity 0)
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tS, make_sdesc(sdS + kk * 2048, 16384, 1024), make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt,
+                  kk != 0);
+        umma_commit(bar_e);  // completion #3 (parity 0)
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
@@ -305,7 +339,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int j = 0; j < W; ++j) gw[j] = 0.f;
     const float sc = a.scale_log2;
     for (int j = 0; j < num_tiles; ++j) {
+      if (row == 0 && half == 0) AB_TRACE(0, 1, j, 0);
       mbar_wait(bar_s, j & 1);
+      if (row == 0 && half == 0) AB_TRACE(0, 1, j, 1);
       tc_fence_after();
       float hb[RH], gh[RH];
 #pragma unroll
@@ -364,9 +400,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int i = j * R + half * RH + r;
         if (i < h) my_gh[i] = gh[r];
       }
+      if (row == 0 && half == 0) AB_TRACE(0, 1, j, 2);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (row == 0 && half == 0) AB_TRACE(0, 1, j, 3);
     }
 
     // ---------------- epilogue phase 1: Gh^ x 8 (bf16, K-major / MN-major dual view) ----------------
@@ -517,7 +556,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(bar_qe, 1);
     mbar_init(bar_qe + 8, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, AB_SMX);
+    mbar_init(bar_p, AB_SMX / 32);
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
@@ -542,36 +581,47 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
       const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
       mbar_wait(bar_kv, 0);
+      const uint64_t dK0 = make_sdesc(sK, 16, 1024), dV0 = make_sdesc(sV, 16, 1024);
+      const uint64_t dP0 = make_sdesc(sP, 16384, 1024), ddS0 = make_sdesc(sdS, 16384, 1024);
       for (int i = 0; i < num_q; ++i) {
         const int st = i & 1;
         const uint32_t sQ = sQ0 + st * 32768, sdO = sQ + 16384;
+        const uint64_t dQ0 = make_sdesc(sQ, 16, 1024), ddO0 = make_sdesc(sdO, 16, 1024);
+        AB_TRACE(1, 0, i, 0);
         mbar_wait(bar_qf + 8 * st, (i >> 1) & 1);
+        AB_TRACE(1, 0, i, 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sK + k * 32, 16, 1024), idesc_s, k != 0);
+          for (int k = 0; k < 4; ++k) umma_ss(tS, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tdP, make_sdesc(sdO + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc_s, k != 0);
-        umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k) umma_ss(tdP, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
+        AB_TRACE(1, 0, i, 2);
         mbar_wait(bar_p, i & 1);
+        AB_TRACE(1, 0, i, 3);
         tc_fence_after();
         // dV[keys, d] += P^T . dO ;  dK[keys, d] += dS^T . Q   (A: MN-major view of the [q rows][keys] tiles)
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tdV, make_sdesc(sP + kk * 2048, 16384, 1024), make_sdesc(sdO + kk * 2048, 16, 1024), idesc_tt,
-                  (i | kk) != 0);
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tdV, sdesc_add(dP0, kk * 2048), sdesc_add(ddO0, kk * 2048), idesc_tt, (i | kk) != 0);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tdK, make_sdesc(sdS + kk * 2048, 16384, 1024), make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt,
-                  (i | kk) != 0);
-        umma_commit(bar_qe + 8 * st);
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tdK, sdesc_add(ddS0, kk * 2048), sdesc_add(dQ0, kk * 2048), idesc_tt, (i | kk) != 0);
+          umma_commit(bar_qe + 8 * st);
+        }
+        __syncwarp();
+        AB_TRACE(1, 0, i, 4);
       }
-      umma_commit(bar_o);
+      if (elect_one()) umma_commit(bar_o);
+      __syncwarp();
     }
   } else {
     // 8 softmax warps, same column split as kernel A
@@ -603,7 +653,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < W; ++j) relw[j] = pw[j];
       }
       const bool full = keys_valid >= AB_KT / 2 && valid;
+      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 0);
       mbar_wait(bar_s, i & 1);
+      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 1);
       tc_fence_after();
       const uint32_t tS_h = tS + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
 #pragma unroll
@@ -648,9 +700,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
+      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 2);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 3);
     }
     // epilogue: accumulator row = key (jt*112 + row), rows >= 112 are padding; half 0 writes dK (x 1/8: dS is
     // stored unscaled), half 1 writes dV
@@ -691,6 +746,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 using namespace pk;
 
+static long long* g_attnb_trace = nullptr;
+// debug hook: device buffer of 2*2*16*8 int64 (clock64 timeline of CTA (0,0,0) of both backward kernels)
+extern "C" void pk_attn_bwd_set_trace(void* buf) { g_attnb_trace = static_cast<long long*>(buf); }
+
 // qkv / dqkv: bf16 [B*N, 3C];  O, dO: bf16 [B*N, C];  lse: fp32 [B*heads, N] from pk_attn_fwd
 // scratch buffers (caller-allocated): delta [B*heads*N], relh_g [B*heads*N*h], relw_g [B*heads*N*w] fp32
 // dTh [2h-1, 64], dTw [2w-1, 64]: fp32, accumulated atomically (caller zero-initialises)
@@ -716,6 +775,7 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   a.lse = lse; a.delta = delta; a.relh_g = relh_g; a.relw_g = relw_g;
   a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   a.dTh = dTh; a.dTw = dTw;
+  a.trace = g_attnb_trace;
 
   CUtensorMap tmQ, tmKV, tmdO, tmTh, tmTw;
   {

@@ -45,7 +45,8 @@ struct AttnFwdArgs {
 // debug timeline: role 0 = producer, 1 = MMA issuer, 2 = softmax row 0; 8 events per tile
 #define ATT_TRACE(role, tile, ev)                                                                     \
   do {                                                                                                \
-    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 16)   \
+    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 16 &&   \
+        ((role) == 2 || (threadIdx.x & 31) == 0))                                                       \
       a.trace[((role) * 16 + (tile)) * 8 + (ev)] = clock64();                                          \
   } while (0)
 
@@ -87,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(bar_vf, 1);
     mbar_init(bar_ve, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 4);
     mbar_init(bar_o, 1);
     mbar_init(bar_g, 1);
     mbar_init(bar_gr, 128);
@@ -124,52 +125,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // -------------------------------------- MMA issuer --------------------------------------
+      // The whole warp runs the (uniform) control flow; only the tcgen05 instructions are issued by one elected lane.
       mbar_wait(bar_q, 0);
       tc_fence_after();
       {  // G_w = Q . T_w^T
         const uint32_t idesc = make_idesc_bf16(128, a.tw_pad, false, false);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc, k != 0);
-        umma_commit(bar_g);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc, k != 0);
+          umma_commit(bar_g);
+        }
+        __syncwarp();
       }
       mbar_wait(bar_gr, 0);
       tc_fence_after();
       {  // G_h = Q . T_h^T
         const uint32_t idesc = make_idesc_bf16(128, a.th_pad, false, false);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sP + k * 32, 16, 1024), idesc, k != 0);
-        umma_commit(bar_g);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sP + k * 32, 16, 1024), idesc, k != 0);
+          umma_commit(bar_g);
+        }
+        __syncwarp();
       }
       mbar_wait(bar_gr, 1);
       tc_fence_after();
       const uint32_t idesc_qk = make_idesc_bf16(128, ATT_KT, false, false);
       const uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+      // single-stage operand buffers: every descriptor is loop-invariant
+      uint64_t dq[4], dk[4], dp[ATT_KT / 16], dv[ATT_KT / 16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dq[k] = make_sdesc(sQ + k * 32, 16, 1024);
+        dk[k] = make_sdesc(sK + k * 32, 16, 1024);
+      }
+#pragma unroll
+      for (int kk = 0; kk < ATT_KT / 16; ++kk) {
+        dp[kk] = make_sdesc(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+        dv[kk] = make_sdesc(sV + kk * 2048, 16, 1024);
+      }
       for (int j = 0; j < num_tiles; ++j) {
         ATT_TRACE(1, j, 0);
         mbar_wait(bar_kf, j & 1);
         ATT_TRACE(1, j, 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sK + k * 32, 16, 1024), idesc_qk, k != 0);
-        umma_commit(bar_ke);
-        umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k) umma_ss(tS, dq[k], dk[k], idesc_qk, k != 0);
+          umma_commit(bar_ke);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
         ATT_TRACE(1, j, 2);
-        mbar_wait(bar_p, j & 1);
+        mbar_wait(bar_vf, j & 1);   // completes long before P is ready
         ATT_TRACE(1, j, 3);
-        mbar_wait(bar_vf, j & 1);
+        mbar_wait(bar_p, j & 1);
         ATT_TRACE(1, j, 4);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_KT / 16; ++kk)
-          umma_ss(tO, make_sdesc(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                  make_sdesc(sV + kk * 2048, 16, 1024), idesc_pv, (j | kk) != 0);
-        umma_commit(bar_ve);
-        if (j == num_tiles - 1) umma_commit(bar_o);
+          for (int kk = 0; kk < ATT_KT / 16; ++kk) umma_ss(tO, dp[kk], dv[kk], idesc_pv, (j | kk) != 0);
+          umma_commit(bar_ve);
+          if (j == num_tiles - 1) umma_commit(bar_o);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -322,7 +345,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (row == 0) ATT_TRACE(2, j, 2);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
       if (row == 0) ATT_TRACE(2, j, 3);
     }
     // ---------------- epilogue: O / l -> bf16, LSE ----------------

@@ -27,6 +27,16 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// One elected lane of a fully converged warp (elect.sync): keeps the surrounding control flow warp-uniform so that
+// ptxas can hold MMA / TMA descriptors in uniform registers instead of R2UR-ing them per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------- mbarrier --------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -155,6 +165,10 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
   d |= 1ull << 46;  // descriptor version (sm_100)
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
+}
+// Advance a descriptor's start address by `bytes` (multiple of 16; stays inside the 14-bit field for any smem offset).
+__device__ __forceinline__ uint64_t sdesc_add(uint64_t desc, uint32_t bytes) {
+  return desc + static_cast<uint64_t>(bytes >> 4);
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major,

@@ -228,57 +228,87 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
   }
   __syncwarp();
   // ---- phase 2 (lane = 4 consecutive columns; 8 lanes per row, 4 rows per instruction) ----
+  // staged values first, then all the math (32 independent elements per lane -> ILP), then all the stores
+  float4 xs[8];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + rsub;
-    const int row = row0 + r;
-    float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
-    if (row >= M) continue;
-    const size_t off = static_cast<size_t>(row) * e.ldc + cc;
-    if constexpr (KIND == PK_EPI_BF16) {
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(x);
-    } else if constexpr (KIND == PK_EPI_F32) {
-      float* d = reinterpret_cast<float*>(e.out) + off;
-      if (e.accumulate == 2) {  // split-K partials
-        atomicAdd(d + 0, x.x);
-        atomicAdd(d + 1, x.y);
-        atomicAdd(d + 2, x.z);
-        atomicAdd(d + 3, x.w);
+  for (int it = 0; it < 8; ++it) xs[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * STG_LD + c4);
+  __syncwarp();  // the staging tile may be overwritten by the next chunk from here on
+
+  if constexpr (KIND == PK_EPI_BF16 || KIND == PK_EPI_PIXSHUF) {
+    uint2 o[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) o[it] = pack4_bf16(xs[it]);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + rsub;
+      if (row >= M) continue;
+      size_t off;
+      if constexpr (KIND == PK_EPI_BF16) {
+        off = static_cast<size_t>(row) * e.ldc + cc;
       } else {
-        if (e.accumulate == 1) {
-          x.x += auxf[it].x; x.y += auxf[it].y; x.z += auxf[it].z; x.w += auxf[it].w;
-        }
-        *reinterpret_cast<float4*>(d) = x;
+        const int hw = e.ps_h * e.ps_w;
+        const int b = row / hw, t = row - b * hw;
+        const int i = t / e.ps_w, j = t - i * e.ps_w;
+        const int pc = e.ps_p * e.ps_c;
+        const int rr = cc / pc, rem = cc - rr * pc;
+        const int ss = rem / e.ps_c, c = rem - ss * e.ps_c;
+        off = ((static_cast<size_t>(b) * (e.ps_h * e.ps_p) + i * e.ps_p + rr) * (static_cast<size_t>(e.ps_w) * e.ps_p) +
+               j * e.ps_p + ss) * e.ps_c + c;
       }
-    } else if constexpr (KIND == PK_EPI_GELU) {
-      const uint2 zb = pack4_bf16(x);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = zb;
-      const float4 zr = unpack4_bf16(zb);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + off) =
-          pack4_bf16(make_float4(gelu_erf(zr.x), gelu_erf(zr.y), gelu_erf(zr.z), gelu_erf(zr.w)));
-    } else if constexpr (KIND == PK_EPI_RESID) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) =
-          make_float4(x.x + auxf[it].x, x.y + auxf[it].y, x.z + auxf[it].z, x.w + auxf[it].w);
-    } else if constexpr (KIND == PK_EPI_DGELU) {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = o[it];
+    }
+  } else if constexpr (KIND == PK_EPI_F32 || KIND == PK_EPI_RESID) {
+    if (KIND == PK_EPI_RESID || e.accumulate == 1) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        xs[it].x += auxf[it].x; xs[it].y += auxf[it].y; xs[it].z += auxf[it].z; xs[it].w += auxf[it].w;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + rsub;
+      if (row >= M) continue;
+      float* d = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldc + cc;
+      if (KIND == PK_EPI_F32 && e.accumulate == 2) {  // split-K partials
+        atomicAdd(d + 0, xs[it].x);
+        atomicAdd(d + 1, xs[it].y);
+        atomicAdd(d + 2, xs[it].z);
+        atomicAdd(d + 3, xs[it].w);
+      } else {
+        *reinterpret_cast<float4*>(d) = xs[it];
+      }
+    }
+  } else if constexpr (KIND == PK_EPI_GELU) {
+    uint2 zb[8], hb[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      zb[it] = pack4_bf16(xs[it]);
+      const float4 zr = unpack4_bf16(zb[it]);
+      hb[it] = pack4_bf16(make_float4(gelu_erf(zr.x), gelu_erf(zr.y), gelu_erf(zr.z), gelu_erf(zr.w)));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + rsub;
+      if (row >= M) continue;
+      const size_t off = static_cast<size_t>(row) * e.ldc + cc;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = zb[it];
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out2) + off) = hb[it];
+    }
+  } else if constexpr (KIND == PK_EPI_DGELU) {
+    uint2 o[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
       const float4 z = unpack4_bf16(auxh[it]);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = pack4_bf16(make_float4(
-          x.x * gelu_erf_grad(z.x), x.y * gelu_erf_grad(z.y), x.z * gelu_erf_grad(z.z), x.w * gelu_erf_grad(z.w)));
-    } else if constexpr (KIND == PK_EPI_PIXSHUF) {
-      const int hw = e.ps_h * e.ps_w;
-      const int b = row / hw, t = row - b * hw;
-      const int i = t / e.ps_w, j = t - i * e.ps_w;
-      const int pc = e.ps_p * e.ps_c;
-      const int rr = cc / pc, rem = cc - rr * pc;
-      const int ss = rem / e.ps_c, c = rem - ss * e.ps_c;
-      const size_t o = ((static_cast<size_t>(b) * (e.ps_h * e.ps_p) + i * e.ps_p + rr) *
-                            (static_cast<size_t>(e.ps_w) * e.ps_p) +
-                        j * e.ps_p + ss) *
-                           e.ps_c +
-                       c;
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + o) = pack4_bf16(x);
+      o[it] = pack4_bf16(make_float4(xs[it].x * gelu_erf_grad(z.x), xs[it].y * gelu_erf_grad(z.y),
+                                     xs[it].z * gelu_erf_grad(z.z), xs[it].w * gelu_erf_grad(z.w)));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row0 + it * 4 + rsub;
+      if (row >= M) continue;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + static_cast<size_t>(row) * e.ldc + cc) = o[it];
     }
   }
-  __syncwarp();
 }
 
 template <int KIND>
@@ -388,8 +418,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ------------------------------- MMA issuer -------------------------------
+      // warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues tcgen05
       const uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, g.transA != 0, g.transB != 0);
       uint32_t s = 0, ph = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -405,21 +436,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t a_addr = sA + s * GEMM_A_BYTES;
           const uint32_t b_addr = sB + s * B_BYTES;
+          const uint64_t a0 = g.transA ? make_sdesc(a_addr, 8192, 1024) : make_sdesc(a_addr, 16, 1024);
+          const uint64_t b0 = g.transB ? make_sdesc(b_addr, 8192, 1024) : make_sdesc(b_addr, 16, 1024);
+          const uint32_t a_step = g.transA ? 2048u : 32u, b_step = g.transB ? 2048u : 32u;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t adesc = g.transA ? make_sdesc(a_addr + k * 2048, 8192, 1024)
-                                            : make_sdesc(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = g.transB ? make_sdesc(b_addr + k * 2048, 8192, 1024)
-                                            : make_sdesc(b_addr + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_ss(d_tmem, sdesc_add(a0, k * a_step), sdesc_add(b0, k * b_step), idesc,
+                      (kb != kb0 || k != 0) ? 1u : 0u);
+            umma_commit(empty_bar(s));
           }
-          umma_commit(empty_bar(s));
+          __syncwarp();
           if (++s == static_cast<uint32_t>(stages)) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(tfull_bar(as));
+        if (elect_one()) umma_commit(tfull_bar(as));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -26,3 +26,22 @@ for j in range(14):
             v = int(t[role, j, e])
             line += f"{'PMS'[role] if False else ['prod','mma','smx'][role]}.{nm}={v - t0 if v else -1:7d} "
     print(line)
+
+# ---- backward kernels ----
+out, lse = ops.attn_fwd(qkv, th, tw, B, heads, h, w)
+do = (torch.randn(B * N, C, device="cuda") * 0.5).bfloat16()
+for _ in range(2):
+    ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w)
+buf2 = torch.zeros(2 * 2 * 16 * 8, dtype=torch.int64, device="cuda")
+_lib.lib().pk_attn_bwd_set_trace(ctypes.c_void_p(buf2.data_ptr()))
+ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w)
+torch.cuda.synchronize()
+_lib.lib().pk_attn_bwd_set_trace(None)
+t2 = buf2.cpu().view(2, 2, 16, 8)
+for kern, kn in ((0, "dq "), (1, "dkv")):
+    t0 = int(t2[kern, 0, 0, 0])
+    for j in range(14 if kern == 0 else 13):
+        m = [int(t2[kern, 0, j, e]) - t0 for e in range(5)]
+        sx = [int(t2[kern, 1, j, e]) - t0 for e in range(4)]
+        print(f"{kn} it {j:2d}: mma top={m[0]:7d} ld_seen={m[1]:7d} sdp_issued={m[2]:7d} p_seen={m[3]:7d} "
+              f"acc_issued={m[4]:7d} | smx wait={sx[0]:7d} s_seen={sx[1]:7d} done={sx[2]:7d} arrived={sx[3]:7d}")

@@ -86,16 +86,18 @@ def test_gemm_pixel_shuffle_epilogue_matches_reference_einsum():
 
 
 def test_gemm_linearity_at_full_size():
-    """Size-independent property at the BASELINE geometry (qkv projection, M = 12544): f(a1 + a2) = f(a1) + f(a2)."""
+    """Size-independent property at the BASELINE geometry (qkv projection, M = 12544): f(a1 + a2) = f(a1) + f(a2).
+    Small-integer operands make every product and partial sum exact in fp32, so the identity must hold BIT-EXACTLY
+    whatever the accumulation order of the tensor cores."""
     from painter_b200 import ops
     M, N, K = 12544, 3072, 1024
-    a1 = torch.randn(M, K, device=DEV).bfloat16()
-    a2 = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
-    s = (a1.float() + a2.float()).bfloat16()
-    a2 = (s.float() - a1.float()).bfloat16()          # make the bf16 sum exact
-    b = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    a1 = torch.randint(-4, 5, (M, K), device=DEV).bfloat16()
+    a2 = torch.randint(-4, 5, (M, K), device=DEV).bfloat16()
+    b = (torch.randint(-4, 5, (N, K), device=DEV).float() / 8).bfloat16()
     f = lambda x: ops.gemm(x, b, kind=ops.EPI_F32)
-    assert relmax(f((a1.float() + a2.float()).bfloat16()), f(a1) + f(a2)) < 1e-5
+    lhs, rhs = f((a1.float() + a2.float()).bfloat16()), f(a1) + f(a2)
+    assert torch.equal(lhs, rhs)
+    assert torch.equal(f(a1)[:64], a1[:64].float() @ b.float().t())
 
 
 # ------------------------------------------------------------ streaming kernels --------------------------------

@@ -67,6 +67,8 @@ int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, int lda, int
 /* test hooks: force the GEMM N-tile (64/128/256) or split-K factor; 0 restores the heuristics */
 void pk_gemm_force_bn(int bn);
 void pk_gemm_force_splits(int s);
+/* 0 = single-CTA tiles (128 x BN), 1 = CTA pairs / cta_group::2 (256 x BN) whenever the shape allows */
+void pk_gemm_use_2cta(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over channels (nn.LayerNorm(eps=1e-6): models_painter.py:193,200 norm1/norm2, :315,:417 final norm).

@@ -97,7 +97,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int h = a.h;
   const int num_tiles = (h + R - 1) / R;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmdO);
@@ -115,14 +115,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_t, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(holder, 512);
+  if (warp == 9) tmem_alloc(holder, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
   const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       // ------------------------------------ TMA producer ------------------------------------
       mbar_expect_tx(bar_q, 32768u + static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u);
@@ -144,7 +144,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(sTh, &tmTh, bar_t, 0, 0);
       tma_load_2d(sTw, &tmTw, bar_t, 0, 0);
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     {
       // -------------------------------------- MMA issuer --------------------------------------
       // warp-uniform control flow; the tcgen05 instructions themselves are issued by one elected lane
@@ -245,12 +245,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
-    // 8 warps: warps 2..5 own key columns [0,56) of every tile, warps 6..9 columns [56,112); the two warps with
+    // 8 warps: warps 0..3 own key columns [0,56) of every tile, warps 4..7 columns [56,112) (warp 8 = TMA, warp 9 =
+    // MMA issuer: highest ids win the issue arbitration, they are the critical path); the two warps with
     // the same (warp & 3) share the 32 TMEM lanes (= query rows) of that quarter.
     constexpr int RH = R / 2;  // image rows per half tile (56 % W == 0 for every supported W)
     static_assert(RH * 2 == R && (AB_KT / 2) % W == 0, "tile halves must be whole image rows");
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = warp >> 2;
     const int cbase = half * (AB_KT / 2);
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
@@ -510,7 +511,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
 // ================================================================================================
@@ -546,7 +547,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int h = a.h;
   const int num_q = (a.N + AB_BM - 1) / AB_BM;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmdO);
@@ -560,14 +561,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(holder, 512);
+  if (warp == 9) tmem_alloc(holder, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(bar_kv, 2 * AB_KT * 128);
       tma_load_3d(sK, &tmKV, bar_kv, C + head * 64, jt * AB_KT, b);
@@ -580,7 +581,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_load_3d(sQ0 + st * 32768 + 16384, &tmdO, bar_qf + 8 * st, head * 64, i * AB_BM, b);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     {
       const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
       const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
@@ -627,7 +628,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // 8 softmax warps, same column split as kernel A
     constexpr int RH = R / 2;
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = warp >> 2;
     const int cbase = half * (AB_KT / 2);
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
@@ -739,7 +740,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pk

@@ -51,6 +51,7 @@ def run_case(name, M, N, K, ta, tb, kind, bn):
     b_in = b.t().contiguous() if tb else b
     ref = a.float() @ b.float().t()
     _lib.lib().pk_gemm_force_bn(bn)
+    _lib.lib().pk_gemm_use_2cta(int(os.environ.get("PK_2CTA", "0")))
     bias = torch.randn(N, device=dev)
     kw = {}
     if kind == "bf16":

@@ -36,13 +36,12 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // smem map (offsets from the 1024-aligned base)
 constexpr uint32_t A_SQ = 0;                    // Q tile 128 x 128 B
 constexpr uint32_t A_SDO = 16384;               // dO tile
-constexpr uint32_t A_SDS = 32768;               // dS tile (2 K-blocks); T_h staged here in the prologue;
-                                                // epilogue: G^ buffer (up to 4 K-blocks = 64 KiB from here)
-constexpr uint32_t A_SKV = A_SDS + 32768;       // 2 stages x (K 14336 | V 14336)
-constexpr uint32_t A_STH = A_SDS + 65536;       // epilogue: T_h reload (<= 28 KiB), after the 64 KiB G^ buffer
-constexpr uint32_t A_STW = A_STH + 28672;       // epilogue: T_w reload (<= 14 KiB)
-constexpr uint32_t A_SRELH = A_STW + 14336;     // rel_h rows fp32 [128][h+1]; Gh' sums overwrite them in place
-static_assert(A_SKV + 57344 <= A_SRELH, "K/V stages must end before the rel_h region");
+constexpr uint32_t A_SDS = 32768;               // 2 x dS tile (2 K-blocks each, double-buffered); T_h staged in
+                                                // buffer 0 during the prologue; epilogue: G^ buffer (<= 4 K-blocks)
+constexpr uint32_t A_SKV = A_SDS + 65536;       // 2 stages x (K 14336 | V 14336)
+constexpr uint32_t A_STH = A_SKV;               // epilogue: T_h reload (<= 28 KiB) over stage 0
+constexpr uint32_t A_STW = A_SKV + 28672;       // epilogue: T_w reload (<= 14 KiB) over stage 1
+constexpr uint32_t A_SRELH = A_SKV + 57344;     // rel_h rows fp32 [128][h+1]; Gh' sums overwrite them in place
 
 struct AttnBwdArgs {
   int h, N, heads;
@@ -83,12 +82,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t sTh = base + A_STH, sTw = base + A_STW;
   float* relh_gen = reinterpret_cast<float*>(gen + A_SRELH);
   const uint32_t bar0 = base + A_SRELH + a.relh_bytes;
-  const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*2*/, bar_ke = bar0 + 24 /*2*/, bar_s = bar0 + 40,
-                 bar_p = bar0 + 48, bar_g = bar0 + 56, bar_gr = bar0 + 64, bar_e = bar0 + 72,
-                 bar_er = bar0 + 80, bar_t = bar0 + 88;
-  const uint32_t holder = bar0 + 96;
+  const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*2*/, bar_ke = bar0 + 24 /*2*/, bar_s = bar0 + 40 /*2*/,
+                 bar_p = bar0 + 56, bar_g = bar0 + 64, bar_gr = bar0 + 72, bar_e = bar0 + 80,
+                 bar_er = bar0 + 88, bar_t = bar0 + 96;
+  const uint32_t holder = bar0 + 104;
   volatile uint32_t* holder_gen =
-      reinterpret_cast<volatile uint32_t*>(gen + A_SRELH + a.relh_bytes + 96);
+      reinterpret_cast<volatile uint32_t*>(gen + A_SRELH + a.relh_bytes + 104);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AB_BM;
@@ -107,6 +106,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_ke, 1);
     mbar_init(bar_ke + 8, 1);
     mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
     mbar_init(bar_p, AB_SMX / 32);
     mbar_init(bar_g, 1);
     mbar_init(bar_gr, AB_SMX);
@@ -120,7 +120,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+  // S / dP double-buffered: buffer b at columns 224 b (S) and 224 b + 112 (dP); dQ accumulator at 448
+  const uint32_t tS = tmem, tdQ = tmem + 448;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -178,27 +179,35 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
       const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
       const uint64_t dQ0 = make_sdesc(sQ, 16, 1024), ddO0 = make_sdesc(sdO, 16, 1024);
-      const uint64_t ddS0 = make_sdesc(sdS, 16, 1024);
-      for (int j = 0; j < num_tiles; ++j) {
+      // software pipeline: S/dP of tile j+1 are issued before waiting for dS of tile j, so the tensor core works
+      // on the next scores while the softmax warps chew on the current ones
+      auto issue_scores = [&](int j) {
         const int st = j & 1;
         const uint32_t sK = sKV + st * 28672, sV = sK + 14336;
         const uint64_t dK0 = make_sdesc(sK, 16, 1024), dV0 = make_sdesc(sV, 16, 1024);
-        AB_TRACE(0, 0, j, 0);
+        const uint32_t tSb = tS + st * 224, tdPb = tSb + 112;
         mbar_wait(bar_kf + 8 * st, (j >> 1) & 1);
-        AB_TRACE(0, 0, j, 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
+          for (int k = 0; k < 4; ++k) umma_ss(tSb, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tdP, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
-          umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k) umma_ss(tdPb, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
+          umma_commit(bar_s + 8 * st);
         }
         __syncwarp();
+      };
+      issue_scores(0);
+      for (int j = 0; j < num_tiles; ++j) {
+        const int st = j & 1;
+        AB_TRACE(0, 0, j, 0);
+        if (j + 1 < num_tiles) issue_scores(j + 1);
         AB_TRACE(0, 0, j, 2);
         mbar_wait(bar_p, j & 1);
         AB_TRACE(0, 0, j, 3);
         tc_fence_after();
+        const uint64_t ddS0 = make_sdesc(sdS + st * 32768, 16, 1024);
+        const uint64_t dK0 = make_sdesc(sKV + st * 28672, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < AB_KT / 16; ++kk)
@@ -341,7 +350,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float sc = a.scale_log2;
     for (int j = 0; j < num_tiles; ++j) {
       if (row == 0 && half == 0) AB_TRACE(0, 1, j, 0);
-      mbar_wait(bar_s, j & 1);
+      mbar_wait(bar_s + 8 * (j & 1), (j >> 1) & 1);
       if (row == 0 && half == 0) AB_TRACE(0, 1, j, 1);
       tc_fence_after();
       float hb[RH], gh[RH];
@@ -353,7 +362,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       const int keys_valid = (h - j * R) * W - cbase;  // columns of this half that are real keys
       const bool full = keys_valid >= AB_KT / 2 && valid;
-      const uint32_t tS_h = tS + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
+      const uint32_t tS_h = tS + (j & 1) * 224 + lane_addr + cbase, tdP_h = tS_h + 112;
+      const uint32_t sdS_j = sdS + (j & 1) * 32768;
       // 56 columns per thread: 16 + 16 + 16 + 8
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
@@ -390,7 +400,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int q = 0; q < 2; ++q) {
           if (q * 8 < nc) {
             const int g8 = ((cbase + c0) >> 3) + q;  // 8-column group inside the 112-wide tile
-            st_shared_v4(sdS + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4),
+            st_shared_v4(sdS_j + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4),
                          pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]), pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]),
                          pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]), pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
           }

@@ -233,7 +233,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 int g_force_bn = 0;
 int g_force_splits = 0;
-int g_use_2cta = 0;  // 0 = 1-CTA kernel only, 1 = CTA pairs (gemm2.cu) whenever the shape allows
+int g_use_2cta = 1;  // 1 = CTA pairs (gemm2.cu) whenever the shape allows (default), 0 = 1-CTA kernel only
 
 int launch_gemm2(const void* A, const void* B, int lda, int ldb, GemmArgs& g, cudaStream_t st);
 

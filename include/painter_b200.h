@@ -74,12 +74,14 @@ void pk_gemm_use_2cta(int on);
  * LayerNorm over channels (nn.LayerNorm(eps=1e-6): models_painter.py:193,200 norm1/norm2, :315,:417 final norm).
  * x fp32 [M, C] (row stride ldx) -> out (bf16 if out_is_bf16 else fp32; row stride ldo, so it can be a column
  * slice of the [M, 4C] decoder input, models_painter.py:422); mean/rstd [M] saved for backward (nullable).
- * bwd: dx = LN'(dy) (+ dres), dgamma/dbeta accumulated atomically (caller zero-initialises).              */
+ * bwd: dx = LN'(dy) (+ dres); dgamma/dbeta += column sums (caller initialises; deterministic two-stage
+ * reduction through `workspace`).                                                                         */
 int pk_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, float eps, void* out,
                      int ldo, int out_is_bf16, float* mean, float* rstd, int M, int C, void* stream);
+long long pk_layernorm_bwd_ws_floats(int M, int C); /* fp32 elements of `workspace` (per-block partial sums) */
 int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* mean, const float* rstd,
-                     const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta, int M,
-                     int C, void* stream);
+                     const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta,
+                     float* workspace, int M, int C, void* stream);
 
 /* PatchEmbed lowering (util/vitdet_utils.py:178-186, models_painter.py:387-388): rows of (c,r,s)-ordered
  * patches of imgs then tgts, bf16 [2*B*h*w, Cin*p*p]; the conv itself is pk_gemm_bf16 on these rows.       */

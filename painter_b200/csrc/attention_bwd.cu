@@ -58,6 +58,7 @@ struct AttnBwdArgs {
   float* dTh;                // [2h-1, 64] fp32 atomics
   float* dTw;                // [2W-1, 64]
   long long* trace;          // optional debug timeline of CTA (0,0,0): [kernel][role][iter][event]
+  int debug;                 // bit 0: disable the software pipelining of kernel A (bring-up aid)
 };
 
 #define AB_TRACE(kern, role, it, ev)                                                                       \
@@ -201,7 +202,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = 0; j < num_tiles; ++j) {
         const int st = j & 1;
         AB_TRACE(0, 0, j, 0);
-        if (j + 1 < num_tiles) issue_scores(j + 1);
+        if (j + 1 < num_tiles && !(a.debug & 1)) issue_scores(j + 1);
         AB_TRACE(0, 0, j, 2);
         mbar_wait(bar_p, j & 1);
         AB_TRACE(0, 0, j, 3);
@@ -217,6 +218,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __syncwarp();
         AB_TRACE(0, 0, j, 4);
+        if (j + 1 < num_tiles && (a.debug & 1)) issue_scores(j + 1);
       }
       if (elect_one()) umma_commit(bar_e);  // completion #1 (parity 0): main loop retired
       __syncwarp();
@@ -335,13 +337,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      mbar_arrive(bar_gr);
-      if (valid && half == 0) {
+      if (valid && half == 0) {  // before the arrive: afterwards the other half may overwrite rel_h rows with Gh'
         float* dst = a.relh_g + (bh * a.N + t) * h;
         for (int i = 0; i < h; ++i) dst[i] = my_relh[i];
       }
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive(bar_gr);
     }
 
     float gw[W];
@@ -530,9 +532,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr uint32_t B_SK = 0;                 // K tile 112 x 128 B
 constexpr uint32_t B_SV = 14336;             // V tile
 constexpr uint32_t B_SQ = 28672;             // 2 stages x (Q 16384 | dO 16384)
-constexpr uint32_t B_SP = B_SQ + 65536;      // P tile  (2 K-blocks)
-constexpr uint32_t B_SDS = B_SP + 32768;     // dS tile (2 K-blocks)
-constexpr uint32_t B_BARS = B_SDS + 32768;
+constexpr uint32_t B_SP = B_SQ + 65536;      // 2 x P tile  (2 K-blocks each, double-buffered)
+constexpr uint32_t B_SDS = B_SP + 65536;     // 2 x dS tile
+constexpr uint32_t B_BARS = B_SDS + 65536;
 
 template <int W>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -545,10 +547,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* gen = smem_raw + (base - raw_base);
   const uint32_t sK = base + B_SK, sV = base + B_SV, sQ0 = base + B_SQ, sP = base + B_SP, sdS = base + B_SDS;
   const uint32_t bar0 = base + B_BARS;
-  const uint32_t bar_kv = bar0, bar_qf = bar0 + 8 /*2*/, bar_qe = bar0 + 24 /*2*/, bar_s = bar0 + 40,
-                 bar_p = bar0 + 48, bar_o = bar0 + 56;
-  const uint32_t holder = bar0 + 64;
-  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B_BARS + 64);
+  const uint32_t bar_kv = bar0, bar_qf = bar0 + 8 /*2*/, bar_qe = bar0 + 24 /*2*/, bar_s = bar0 + 40 /*2*/,
+                 bar_p = bar0 + 56, bar_o = bar0 + 64, bar_dp = bar0 + 72;
+  const uint32_t holder = bar0 + 80;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B_BARS + 80);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x;  // key tile
@@ -567,6 +569,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(bar_qe, 1);
     mbar_init(bar_qe + 8, 1);
     mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
+    mbar_init(bar_dp, 1);
     mbar_init(bar_p, AB_SMX / 32);
     mbar_init(bar_o, 1);
     fence_barrier_init();
@@ -576,7 +580,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
+  // S double-buffered (columns 0 / 112), dP single (224), dV (336), dK (400)
+  const uint32_t tS = tmem, tdP = tmem + 224, tdV = tmem + 336, tdK = tmem + 400;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -597,27 +602,43 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
       mbar_wait(bar_kv, 0);
       const uint64_t dK0 = make_sdesc(sK, 16, 1024), dV0 = make_sdesc(sV, 16, 1024);
-      const uint64_t dP0 = make_sdesc(sP, 16384, 1024), ddS0 = make_sdesc(sdS, 16384, 1024);
-      for (int i = 0; i < num_q; ++i) {
+      // Pipeline: S(i+1) is issued while the softmax warps work on tile i; dP(i+1) right after they hand back
+      // tile i, ahead of the 16 accumulation MMAs of tile i, so the next softmax pass overlaps those.
+      auto issue_s = [&](int i) {
         const int st = i & 1;
-        const uint32_t sQ = sQ0 + st * 32768, sdO = sQ + 16384;
-        const uint64_t dQ0 = make_sdesc(sQ, 16, 1024), ddO0 = make_sdesc(sdO, 16, 1024);
-        AB_TRACE(1, 0, i, 0);
+        const uint64_t dQ0 = make_sdesc(sQ0 + st * 32768, 16, 1024);
         mbar_wait(bar_qf + 8 * st, (i >> 1) & 1);
-        AB_TRACE(1, 0, i, 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tdP, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
-          umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS + st * 112, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
+          umma_commit(bar_s + 8 * st);
         }
         __syncwarp();
+      };
+      auto issue_dp = [&](int i) {
+        const uint64_t ddO0 = make_sdesc(sQ0 + (i & 1) * 32768 + 16384, 16, 1024);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tdP, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
+          umma_commit(bar_dp);
+        }
+        __syncwarp();
+      };
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < num_q; ++i) {
+        const int st = i & 1;
+        AB_TRACE(1, 0, i, 0);
+        if (i + 1 < num_q) issue_s(i + 1);
         AB_TRACE(1, 0, i, 2);
         mbar_wait(bar_p, i & 1);
         AB_TRACE(1, 0, i, 3);
         tc_fence_after();
+        if (i + 1 < num_q) issue_dp(i + 1);
+        const uint64_t dQ0 = make_sdesc(sQ0 + st * 32768, 16, 1024), ddO0 = make_sdesc(sQ0 + st * 32768 + 16384, 16, 1024);
+        const uint64_t dP0 = make_sdesc(sP + st * 32768, 16384, 1024), ddS0 = make_sdesc(sdS + st * 32768, 16384, 1024);
         // dV[keys, d] += P^T . dO ;  dK[keys, d] += dS^T . Q   (A: MN-major view of the [q rows][keys] tiles)
         if (elect_one()) {
 #pragma unroll
@@ -665,10 +686,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       const bool full = keys_valid >= AB_KT / 2 && valid;
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 0);
-      mbar_wait(bar_s, i & 1);
+      mbar_wait(bar_s + 8 * (i & 1), (i >> 1) & 1);
+      mbar_wait(bar_dp, i & 1);
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 1);
       tc_fence_after();
-      const uint32_t tS_h = tS + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
+      const uint32_t tS_h = tS + (i & 1) * 112 + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
+      const uint32_t sP_i = sP + (i & 1) * 32768, sdS_i = sdS + (i & 1) * 32768;
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c0 = ci * 16;
@@ -703,9 +726,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (q * 8 < nc) {
             const int g8 = ((cbase + c0) >> 3) + q;
             const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
-            st_shared_v4(sP + off, pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]), pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]),
+            st_shared_v4(sP_i + off, pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]), pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]),
                          pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5]), pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]));
-            st_shared_v4(sdS + off, pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
+            st_shared_v4(sdS_i + off, pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
                          pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]), pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]),
                          pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
           }
@@ -758,6 +781,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 using namespace pk;
 
 static long long* g_attnb_trace = nullptr;
+static int g_attnb_debug = 0;
+extern "C" void pk_attn_bwd_debug(int flags) { g_attnb_debug = flags; }
 // debug hook: device buffer of 2*2*16*8 int64 (clock64 timeline of CTA (0,0,0) of both backward kernels)
 extern "C" void pk_attn_bwd_set_trace(void* buf) { g_attnb_trace = static_cast<long long*>(buf); }
 
@@ -787,6 +812,7 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   a.dTh = dTh; a.dTw = dTw;
   a.trace = g_attnb_trace;
+  a.debug = g_attnb_debug;
 
   CUtensorMap tmQ, tmKV, tmdO, tmTh, tmTw;
   {

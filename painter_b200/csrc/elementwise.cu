@@ -66,11 +66,11 @@ ln_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ ga
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ dres);  dgamma += dy*xhat; dbeta += dy
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C) {
+              float* __restrict__ partials /* [gridDim.x][2C] */, int M, int C) {
   extern __shared__ float red[];  // [8 warps][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = C / 128;
@@ -118,7 +118,8 @@ ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ 
         dxr[i * 32 + lane] = o;
       }
   }
-  // block reduce of dgamma/dbeta partials, then one atomic per column per block
+  // block reduce of the dgamma/dbeta partials; one row of the partials buffer per block (no atomics: a second
+  // tiny kernel sums the rows)
   float4* sg = reinterpret_cast<float4*>(red) + static_cast<size_t>(warp) * 2 * (C / 4);
   float4* sb = sg + C / 4;
 #pragma unroll
@@ -132,9 +133,19 @@ ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ 
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[static_cast<size_t>(w) * 2 * C + c];
-    if (c < C) atomicAdd(dgamma + c, s);
-    else atomicAdd(dbeta + (c - C), s);
+    partials[static_cast<size_t>(blockIdx.x) * 2 * C + c] = s;
   }
+}
+
+// dgamma[c] += sum_b partials[b][c];  dbeta[c] += sum_b partials[b][C + c]
+__global__ void ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partials[static_cast<size_t>(b) * 2 * C + c];
+  if (c < C) dgamma[c] += s;
+  else dbeta[c - C] += s;
 }
 
 // =============================================================================================
@@ -345,15 +356,30 @@ __global__ void scale_cast_colsum_kernel(const float* __restrict__ in, int ldin,
   const int c4n = C / 4;
   for (int c4 = threadIdx.x; c4 < c4n; c4 += blockDim.x) {
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int row = blockIdx.x; row < M; row += gridDim.x) {
-      const float sc = rowscale ? rowscale[row / rows_per_group] : 1.f;
-      float4 v = reinterpret_cast<const float4*>(in + static_cast<size_t>(row) * ldin)[c4];
-      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
-      reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C)[c4] = u;
+    for (int row0 = blockIdx.x * 4; row0 < M; row0 += gridDim.x * 4) {
+      float4 v[4];
+      float sc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {  // four independent rows in flight per thread
+        const int row = row0 + r;
+        if (row < M) {
+          v[r] = reinterpret_cast<const float4*>(in + static_cast<size_t>(row) * ldin)[c4];
+          sc[r] = rowscale ? rowscale[row / rows_per_group] : 1.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = row0 + r;
+        if (row < M) {
+          float4 t = v[r];
+          t.x *= sc[r]; t.y *= sc[r]; t.z *= sc[r]; t.w *= sc[r];
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          uint2 u;
+          u.x = pack_bf16x2(t.x, t.y);
+          u.y = pack_bf16x2(t.z, t.w);
+          reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C)[c4] = u;
+        }
+      }
     }
     if (colsum) {
       atomicAdd(colsum + c4 * 4 + 0, acc.x); atomicAdd(colsum + c4 * 4 + 1, acc.y);
@@ -460,10 +486,20 @@ extern "C" int pk_layernorm_fwd(const float* x, int ldx, const float* gamma, con
   return 0;
 }
 
+static int ln_bwd_grid(int M) {
+  int grid = sm_count() * 2;
+  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
+  return grid;
+}
+// fp32 workspace elements pk_layernorm_bwd needs (per-block partial sums of dgamma / dbeta)
+extern "C" long long pk_layernorm_bwd_ws_floats(int M, int C) {
+  return static_cast<long long>(ln_bwd_grid(M)) * 2 * C;
+}
+
 extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* mean,
                                 const float* rstd, const float* gamma, const float* dres, float* dx,
-                                float* dgamma, float* dbeta, int M, int C, void* stream) {
-  PK_CHECK(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "pk_layernorm_bwd: null pointer");
+                                float* dgamma, float* dbeta, float* workspace, int M, int C, void* stream) {
+  PK_CHECK(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "pk_layernorm_bwd: null pointer");
   PK_CHECK(C % 128 == 0 && C <= 128 * LN_MAX_V4, "pk_layernorm_bwd: bad C=%d", C);
   const size_t smem = static_cast<size_t>(8) * 2 * C * sizeof(float);
   static bool attr = false;
@@ -471,11 +507,13 @@ extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int l
     cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
     attr = true;
   }
-  int grid = sm_count() * 2;
-  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
+  const int grid = ln_bwd_grid(M);
   ln_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, mean, rstd, gamma,
-                                                                      dres, dx, dgamma, dbeta, M, C);
+                                                                      dres, dx, workspace, M, C);
   PK_LAUNCH_CHECK("pk_layernorm_bwd");
+  ln_bwd_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
+                                                                                         dbeta, C);
+  PK_LAUNCH_CHECK("pk_layernorm_bwd(reduce)");
   return 0;
 }
 
@@ -571,7 +609,7 @@ extern "C" int pk_scale_cast_colsum(const float* in, int ldin, const float* rows
   int tx = C / 4;
   if (tx > 256) tx = 256;
   int grid = sm_count() * 4;
-  if (grid > M) grid = M;
+  if (grid > (M + 3) / 4) grid = (M + 3) / 4;
   scale_cast_colsum_kernel<<<grid, tx, 0, static_cast<cudaStream_t>(stream)>>>(
       in, ldin, rowscale, rows_per_group, static_cast<__nv_bfloat16*>(out_bf16), colsum, M, C);
   PK_LAUNCH_CHECK("pk_scale_cast_colsum");

@@ -212,11 +212,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else {
         float* stg = stg_gen + ew * (32 * STG_LD);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int row0 = m_blk * GEMM_BM + ew * 32;
+        EpiAux auxA, auxB;   // explicit ping-pong (BN is a multiple of 64): keeps both in registers
+        gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN, auxA);
+        for (int c0 = 0; c0 < BN; c0 += 64) {
           uint32_t v[32];
           tmem_ld_x32(taddr + c0, v);
+          gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 32, auxB);
           tmem_wait_ld();
-          gemm_epilogue_chunk<KIND>(g.epi, stg, m_blk * GEMM_BM + ew * 32, g.M, n_blk * BN + c0, v);
+          gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, v, auxA);
+          tmem_ld_x32(taddr + c0 + 32, v);
+          if (c0 + 64 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 64, auxA);
+          tmem_wait_ld();
+          gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0 + 32, v, auxB);
         }
       }
       tc_fence_before();
@@ -324,8 +332,15 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
   const int sms = sm_count();
   const int mt = (M + GEMM_BM - 1) / GEMM_BM;
   int BN = 64;
-  if (N % 256 == 0 && static_cast<long long>(mt) * (N / 256) >= sms) BN = 256;
-  else if (N % 128 == 0 && static_cast<long long>(mt) * (N / 128) >= sms / 2) BN = 128;
+  const bool can_split = epi->kind == PK_EPI_F32 && epi->accumulate == 2;
+  if (can_split) {
+    // weight-gradient GEMMs (K = tokens): take the widest tile and fill the machine with split-K instead of
+    // shrinking the tile
+    BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  } else {
+    if (N % 256 == 0 && static_cast<long long>(mt) * (N / 256) >= sms) BN = 256;
+    else if (N % 128 == 0 && static_cast<long long>(mt) * (N / 128) >= sms / 2) BN = 128;
+  }
   if (g_force_bn > 0 && N % g_force_bn == 0) BN = g_force_bn;
   g.BN = BN;
   g.stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);

@@ -207,11 +207,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + ew * 32;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      EpiAux auxA, auxB;   // explicit ping-pong (BN is a multiple of 64): keeps both in registers
+      gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN, auxA);
+      for (int c0 = 0; c0 < BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld_x32(taddr + c0, v);
+        gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 32, auxB);
         tmem_wait_ld();
-        gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, v);
+        gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, v, auxA);
+        tmem_ld_x32(taddr + c0 + 32, v);
+        if (c0 + 64 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 64, auxA);
+        tmem_wait_ld();
+        gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0 + 32, v, auxB);
       }
       tc_fence_before();
       __syncwarp();

@@ -153,42 +153,55 @@ __device__ __forceinline__ float4 unpack4_bf16(const uint2& u) {
                      __uint_as_float(u.y & 0xFFFF0000u));
 }
 
+// Global reads a chunk's epilogue needs (residual / saved pre-activation / accumulate-into output), in the
+// coalesced phase-2 layout.  Issued one chunk AHEAD of their use so that their latency overlaps the TMEM load,
+// the staging pass and the previous chunk's stores.
+struct EpiAux {
+  float4 f[8];
+  uint2 h[8];
+};
+
 template <int KIND>
-__device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* stg, int row0, int M, int col,
-                                                    const uint32_t (&v)[32]) {
+__device__ __forceinline__ void gemm_epilogue_prefetch(const PkEpilogue& e, int row0, int M, int col, EpiAux& a) {
   const int lane = threadIdx.x & 31;
-  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-  const int cc = col + c4;
-  // ---- phase 0: issue every global read of phase 2 up front (one exposed latency per chunk, not eight) ----
-  float4 auxf[8];
-  uint2 auxh[8];
+  const int rsub = lane >> 3, cc = col + (lane & 7) * 4;
   if constexpr (KIND == PK_EPI_RESID) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = row0 + it * 4 + rsub;
-      auxf[it] = row < M ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.aux) +
-                                                            static_cast<size_t>(row) * e.ld_aux + cc)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      a.f[it] = row < M ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.aux) +
+                                                           static_cast<size_t>(row) * e.ld_aux + cc)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if constexpr (KIND == PK_EPI_DGELU) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = row0 + it * 4 + rsub;
-      auxh[it] = row < M ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) +
-                                                           static_cast<size_t>(row) * e.ld_aux + cc)
-                         : make_uint2(0u, 0u);
+      a.h[it] = row < M ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) +
+                                                          static_cast<size_t>(row) * e.ld_aux + cc)
+                        : make_uint2(0u, 0u);
     }
   } else if constexpr (KIND == PK_EPI_F32) {
     if (e.accumulate == 1) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int row = row0 + it * 4 + rsub;
-        auxf[it] = row < M ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) +
-                                                              static_cast<size_t>(row) * e.ldc + cc)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        a.f[it] = row < M ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) +
+                                                             static_cast<size_t>(row) * e.ldc + cc)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
+}
+
+template <int KIND>
+__device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* stg, int row0, int M, int col,
+                                                    const uint32_t (&v)[32], const EpiAux& aux) {
+  const int lane = threadIdx.x & 31;
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  const int cc = col + c4;
+  const float4 (&auxf)[8] = aux.f;
+  const uint2 (&auxh)[8] = aux.h;
   {
     // ---- phase 1 (thread = accumulator row) ----
     const int row = row0 + lane;

@@ -164,8 +164,11 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
     dx = torch.empty((M, C), dtype=torch.float32, device=x.device)
     if dres is not None:
         assert dres.is_contiguous()
-    check(lib().pk_layernorm_bwd(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma),
-                                 _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), M, C, _stream()),
+    L = lib()
+    L.pk_layernorm_bwd_ws_floats.restype = ctypes.c_longlong
+    ws = torch.empty((int(L.pk_layernorm_bwd_ws_floats(M, C)),), dtype=torch.float32, device=x.device)
+    check(L.pk_layernorm_bwd(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma),
+                             _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), M, C, _stream()),
           "pk_layernorm_bwd")
     return dx
 

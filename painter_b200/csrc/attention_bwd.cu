@@ -38,10 +38,10 @@ constexpr uint32_t A_SQ = 0;                    // Q tile 128 x 128 B
 constexpr uint32_t A_SDO = 16384;               // dO tile
 constexpr uint32_t A_SDS = 32768;               // 2 x dS tile (2 K-blocks each, double-buffered); T_h staged in
                                                 // buffer 0 during the prologue; epilogue: G^ buffer (<= 4 K-blocks)
-constexpr uint32_t A_SKV = A_SDS + 65536;       // 2 stages x (K 14336 | V 14336)
+constexpr uint32_t A_SKV = A_SDS + 65536;       // kv_stages (2 or 3) x (K 14336 | V 14336)
 constexpr uint32_t A_STH = A_SKV;               // epilogue: T_h reload (<= 28 KiB) over stage 0
 constexpr uint32_t A_STW = A_SKV + 28672;       // epilogue: T_w reload (<= 14 KiB) over stage 1
-constexpr uint32_t A_SRELH = A_SKV + 57344;     // rel_h rows fp32 [128][h+1]; Gh' sums overwrite them in place
+// rel_h rows fp32 [128][h+1] follow the K/V stages (Gh' sums overwrite them in place): A_SKV + kv_stages * 28672
 
 struct AttnBwdArgs {
   int h, N, heads;
@@ -59,6 +59,7 @@ struct AttnBwdArgs {
   float* dTw;                // [2W-1, 64]
   long long* trace;          // optional debug timeline of CTA (0,0,0): [kernel][role][iter][event]
   int debug;                 // bit 0: disable the software pipelining of kernel A (bring-up aid)
+  int kv_stages;             // kernel A: K/V ring depth (3 hides the TMA latency; 2 when shared memory is short)
 };
 
 #define AB_TRACE(kern, role, it, ev)                                                                       \
@@ -81,14 +82,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const uint32_t sQ = base + A_SQ, sdO = base + A_SDO, sdS = base + A_SDS, sKV = base + A_SKV;
   const uint32_t sTh = base + A_STH, sTw = base + A_STW;
-  float* relh_gen = reinterpret_cast<float*>(gen + A_SRELH);
-  const uint32_t bar0 = base + A_SRELH + a.relh_bytes;
-  const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*2*/, bar_ke = bar0 + 24 /*2*/, bar_s = bar0 + 40 /*2*/,
-                 bar_p = bar0 + 56, bar_g = bar0 + 64, bar_gr = bar0 + 72, bar_e = bar0 + 80,
-                 bar_er = bar0 + 88, bar_t = bar0 + 96;
-  const uint32_t holder = bar0 + 104;
+  const int KS = a.kv_stages;
+  const uint32_t srelh_off = A_SKV + static_cast<uint32_t>(KS) * 28672u;
+  float* relh_gen = reinterpret_cast<float*>(gen + srelh_off);
+  const uint32_t bar0 = base + srelh_off + a.relh_bytes;
+  const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*3*/, bar_ke = bar0 + 32 /*3*/, bar_s = bar0 + 56 /*2*/,
+                 bar_p = bar0 + 72, bar_g = bar0 + 80, bar_gr = bar0 + 88, bar_e = bar0 + 96,
+                 bar_er = bar0 + 104, bar_t = bar0 + 112;
+  const uint32_t holder = bar0 + 120;
   volatile uint32_t* holder_gen =
-      reinterpret_cast<volatile uint32_t*>(gen + A_SRELH + a.relh_bytes + 104);
+      reinterpret_cast<volatile uint32_t*>(gen + srelh_off + a.relh_bytes + 120);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AB_BM;
@@ -102,10 +105,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmdO);
     mbar_init(bar_q, 1);
-    mbar_init(bar_kf, 1);
-    mbar_init(bar_kf + 8, 1);
-    mbar_init(bar_ke, 1);
-    mbar_init(bar_ke + 8, 1);
+    for (int q = 0; q < 3; ++q) {
+      mbar_init(bar_kf + 8 * q, 1);
+      mbar_init(bar_ke + 8 * q, 1);
+    }
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_p, AB_SMX / 32);
@@ -131,11 +134,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_3d(sQ, &tmQ, bar_q, head * 64, q0, b);
       tma_load_3d(sdO, &tmdO, bar_q, head * 64, q0, b);
       tma_load_2d(sdS, &tmTh, bar_q, 0, 0);                 // T_h: th_pad <= 224 rows -> 28 KiB <= 32 KiB
-      tma_load_2d(sKV + 28672 + 14336, &tmTw, bar_q, 0, 0);  // T_w in the stage-1 V buffer
+      tma_load_2d(sKV + (KS - 1) * 28672 + 14336, &tmTw, bar_q, 0, 0);  // T_w in the last stage's V buffer
       for (int j = 0; j < num_tiles; ++j) {
-        const int st = j & 1;
-        if (j >= 2) mbar_wait(bar_ke + 8 * st, ((j >> 1) - 1) & 1);
-        if (j == 1) mbar_wait(bar_g, 0);  // G_w MMA done with T_w (stage-1 V buffer)
+        const int st = j % KS;
+        if (j >= KS) mbar_wait(bar_ke + 8 * st, ((j / KS) - 1) & 1);
+        if (j == KS - 1) mbar_wait(bar_g, 0);  // G_w MMA done with T_w (last stage's V buffer)
         mbar_expect_tx(bar_kf + 8 * st, 2 * AB_KT * 128);
         tma_load_3d(sKV + st * 28672, &tmKV, bar_kf + 8 * st, C + head * 64, j * AB_KT, b);
         tma_load_3d(sKV + st * 28672 + 14336, &tmKV, bar_kf + 8 * st, 2 * C + head * 64, j * AB_KT, b);
@@ -154,7 +157,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       {  // G_w = Q . T_w^T
         const uint32_t idesc = make_idesc_bf16(128, a.tw_pad, false, false);
-        const uint32_t sT = sKV + 28672 + 14336;
+        const uint32_t sT = sKV + (KS - 1) * 28672 + 14336;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -183,11 +186,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // software pipeline: S/dP of tile j+1 are issued before waiting for dS of tile j, so the tensor core works
       // on the next scores while the softmax warps chew on the current ones
       auto issue_scores = [&](int j) {
-        const int st = j & 1;
-        const uint32_t sK = sKV + st * 28672, sV = sK + 14336;
+        const int st = j & 1, ks = j % KS;
+        const uint32_t sK = sKV + ks * 28672, sV = sK + 14336;
         const uint64_t dK0 = make_sdesc(sK, 16, 1024), dV0 = make_sdesc(sV, 16, 1024);
         const uint32_t tSb = tS + st * 224, tdPb = tSb + 112;
-        mbar_wait(bar_kf + 8 * st, (j >> 1) & 1);
+        mbar_wait(bar_kf + 8 * ks, (j / KS) & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -208,13 +211,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         AB_TRACE(0, 0, j, 3);
         tc_fence_after();
         const uint64_t ddS0 = make_sdesc(sdS + st * 32768, 16, 1024);
-        const uint64_t dK0 = make_sdesc(sKV + st * 28672, 16, 1024);
+        const uint64_t dK0 = make_sdesc(sKV + (j % KS) * 28672, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < AB_KT / 16; ++kk)
             umma_ss(tdQ, sdesc_add(ddS0, (kk >> 2) * 16384 + (kk & 3) * 32), sdesc_add(dK0, kk * 2048), idesc_dq,
                     (j | kk) != 0);
-          umma_commit(bar_ke + 8 * st);
+          umma_commit(bar_ke + 8 * (j % KS));
         }
         __syncwarp();
         AB_TRACE(0, 0, j, 4);
@@ -531,10 +534,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ================================================================================================
 constexpr uint32_t B_SK = 0;                 // K tile 112 x 128 B
 constexpr uint32_t B_SV = 14336;             // V tile
-constexpr uint32_t B_SQ = 28672;             // 2 stages x (Q 16384 | dO 16384)
-constexpr uint32_t B_SP = B_SQ + 65536;      // 2 x P tile  (2 K-blocks each, double-buffered)
-constexpr uint32_t B_SDS = B_SP + 65536;     // 2 x dS tile
-constexpr uint32_t B_BARS = B_SDS + 65536;
+constexpr uint32_t B_SQ = 28672;             // 3 stages x (Q 16384 | dO 16384): deep enough to hide the TMA latency
+constexpr uint32_t B_SP = B_SQ + 98304;      // 2 x P tile  (2 K-blocks each, double-buffered)
+constexpr uint32_t B_SDS = B_SP + 65536;     // dS tile (single: the dK MMAs of tile i are issued first and release it)
+constexpr uint32_t B_BARS = B_SDS + 32768;
 
 template <int W>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -547,10 +550,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* gen = smem_raw + (base - raw_base);
   const uint32_t sK = base + B_SK, sV = base + B_SV, sQ0 = base + B_SQ, sP = base + B_SP, sdS = base + B_SDS;
   const uint32_t bar0 = base + B_BARS;
-  const uint32_t bar_kv = bar0, bar_qf = bar0 + 8 /*2*/, bar_qe = bar0 + 24 /*2*/, bar_s = bar0 + 40 /*2*/,
-                 bar_p = bar0 + 56, bar_o = bar0 + 64, bar_dp = bar0 + 72;
-  const uint32_t holder = bar0 + 80;
-  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B_BARS + 80);
+  const uint32_t bar_kv = bar0, bar_qf = bar0 + 8 /*3*/, bar_qe = bar0 + 32 /*3*/, bar_s = bar0 + 56 /*2*/,
+                 bar_p = bar0 + 72, bar_o = bar0 + 80, bar_dp = bar0 + 88, bar_dsf = bar0 + 96;
+  const uint32_t holder = bar0 + 104;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B_BARS + 104);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x;  // key tile
@@ -564,13 +567,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmdO);
     mbar_init(bar_kv, 1);
-    mbar_init(bar_qf, 1);
-    mbar_init(bar_qf + 8, 1);
-    mbar_init(bar_qe, 1);
-    mbar_init(bar_qe + 8, 1);
+    for (int q = 0; q < 3; ++q) {
+      mbar_init(bar_qf + 8 * q, 1);
+      mbar_init(bar_qe + 8 * q, 1);
+    }
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_dp, 1);
+    mbar_init(bar_dsf, 1);
     mbar_init(bar_p, AB_SMX / 32);
     mbar_init(bar_o, 1);
     fence_barrier_init();
@@ -589,8 +593,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_load_3d(sK, &tmKV, bar_kv, C + head * 64, jt * AB_KT, b);
       tma_load_3d(sV, &tmKV, bar_kv, 2 * C + head * 64, jt * AB_KT, b);
       for (int i = 0; i < num_q; ++i) {
-        const int st = i & 1;
-        if (i >= 2) mbar_wait(bar_qe + 8 * st, ((i >> 1) - 1) & 1);
+        const int st = i % 3;
+        if (i >= 3) mbar_wait(bar_qe + 8 * st, ((i / 3) - 1) & 1);
         mbar_expect_tx(bar_qf + 8 * st, 32768);
         tma_load_3d(sQ0 + st * 32768, &tmQ, bar_qf + 8 * st, head * 64, i * AB_BM, b);
         tma_load_3d(sQ0 + st * 32768 + 16384, &tmdO, bar_qf + 8 * st, head * 64, i * AB_BM, b);
@@ -605,20 +609,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // Pipeline: S(i+1) is issued while the softmax warps work on tile i; dP(i+1) right after they hand back
       // tile i, ahead of the 16 accumulation MMAs of tile i, so the next softmax pass overlaps those.
       auto issue_s = [&](int i) {
-        const int st = i & 1;
-        const uint64_t dQ0 = make_sdesc(sQ0 + st * 32768, 16, 1024);
-        mbar_wait(bar_qf + 8 * st, (i >> 1) & 1);
+        const int qs = i % 3;
+        const uint64_t dQ0 = make_sdesc(sQ0 + qs * 32768, 16, 1024);
+        mbar_wait(bar_qf + 8 * qs, (i / 3) & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ss(tS + st * 112, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
-          umma_commit(bar_s + 8 * st);
+            umma_ss(tS + (i & 1) * 112, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
+          umma_commit(bar_s + 8 * (i & 1));
         }
         __syncwarp();
       };
       auto issue_dp = [&](int i) {
-        const uint64_t ddO0 = make_sdesc(sQ0 + (i & 1) * 32768 + 16384, 16, 1024);
+        const uint64_t ddO0 = make_sdesc(sQ0 + (i % 3) * 32768 + 16384, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss(tdP, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
@@ -629,7 +633,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       issue_s(0);
       issue_dp(0);
       for (int i = 0; i < num_q; ++i) {
-        const int st = i & 1;
+        const int qs = i % 3;
         AB_TRACE(1, 0, i, 0);
         if (i + 1 < num_q) issue_s(i + 1);
         AB_TRACE(1, 0, i, 2);
@@ -637,17 +641,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         AB_TRACE(1, 0, i, 3);
         tc_fence_after();
         if (i + 1 < num_q) issue_dp(i + 1);
-        const uint64_t dQ0 = make_sdesc(sQ0 + st * 32768, 16, 1024), ddO0 = make_sdesc(sQ0 + st * 32768 + 16384, 16, 1024);
-        const uint64_t dP0 = make_sdesc(sP + st * 32768, 16384, 1024), ddS0 = make_sdesc(sdS + st * 32768, 16384, 1024);
-        // dV[keys, d] += P^T . dO ;  dK[keys, d] += dS^T . Q   (A: MN-major view of the [q rows][keys] tiles)
+        const uint64_t dQ0 = make_sdesc(sQ0 + qs * 32768, 16, 1024), ddO0 = make_sdesc(sQ0 + qs * 32768 + 16384, 16, 1024);
+        const uint64_t dP0 = make_sdesc(sP + (i & 1) * 32768, 16384, 1024), ddS0 = make_sdesc(sdS, 16384, 1024);
+        // dK[keys, d] += dS^T . Q first (releases the single dS buffer), then dV[keys, d] += P^T . dO
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tdV, sdesc_add(dP0, kk * 2048), sdesc_add(ddO0, kk * 2048), idesc_tt, (i | kk) != 0);
+            umma_ss(tdK, sdesc_add(ddS0, kk * 2048), sdesc_add(dQ0, kk * 2048), idesc_tt, (i | kk) != 0);
+          umma_commit(bar_dsf);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tdK, sdesc_add(ddS0, kk * 2048), sdesc_add(dQ0, kk * 2048), idesc_tt, (i | kk) != 0);
-          umma_commit(bar_qe + 8 * st);
+            umma_ss(tdV, sdesc_add(dP0, kk * 2048), sdesc_add(ddO0, kk * 2048), idesc_tt, (i | kk) != 0);
+          umma_commit(bar_qe + 8 * qs);
         }
         __syncwarp();
         AB_TRACE(1, 0, i, 4);
@@ -691,7 +696,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 1);
       tc_fence_after();
       const uint32_t tS_h = tS + (i & 1) * 112 + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
-      const uint32_t sP_i = sP + (i & 1) * 32768, sdS_i = sdS + (i & 1) * 32768;
+      const uint32_t sP_i = sP + (i & 1) * 32768, sdS_i = sdS;
+      bool ds_free = i == 0;  // the dK MMAs of tile i-1 must have drained the dS buffer before it is rewritten
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c0 = ci * 16;
@@ -720,6 +726,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (!full && (kc >= keys_valid || !valid)) p[c] = 0.f;
             ds[c] = p[c] * (__uint_as_float(w[c]) - delta);
           }
+        }
+        if (!ds_free) {
+          mbar_wait(bar_dsf, (i - 1) & 1);
+          ds_free = true;
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -833,8 +843,9 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
     b2[1] = tw_pad;
     if (!make_tmap_bf16(&tmTw, tw, 2, d2, s2, b2)) return 3;
   }
-  const size_t smemA = 1024 + A_SRELH + static_cast<size_t>(relh_bytes) + 128;
-  const size_t smemB = 1024 + B_BARS + 128;
+  a.kv_stages = (1024 + A_SKV + 3 * 28672 + static_cast<size_t>(relh_bytes) + 192 <= 227 * 1024) ? 3 : 2;
+  const size_t smemA = 1024 + A_SKV + static_cast<size_t>(a.kv_stages) * 28672 + relh_bytes + 192;
+  const size_t smemB = 1024 + B_BARS + 192;
   PK_CHECK(smemA <= 227 * 1024, "pk_attn_bwd: h=%d needs %zu B of shared memory", h, smemA);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 gridA((N + AB_BM - 1) / AB_BM, heads, B);

@@ -141,18 +141,22 @@ class BlockFn(torch.autograd.Function):
         M, C = x.shape
         dev = x.device
         dx2 = dx2.contiguous()
+        H4 = wfc1.shape[0]
+        # one zero-filled slab for every small reduction target of this block (LN affine grads, bias grads)
+        small = torch.zeros(4 * C + 2 * C + H4 + 3 * C, dtype=torch.float32, device=dev)
+        dn1w, dn1b, dn2w, dn2b = small[0:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
+        dfc2_b, dproj_b = small[4 * C:5 * C], small[5 * C:6 * C]
+        dfc1_b, dqkv_b = small[6 * C:6 * C + H4], small[6 * C + H4:]
         # ---- MLP branch ----
-        dy, dfc2_b = ops.scale_cast_colsum(dx2, drop_m, N)
+        dy, _ = ops.scale_cast_colsum(dx2, drop_m, N, colsum_out=dfc2_b)
         dfc2_w = _wgrad(dy, hact)
         dz = ops.gemm(dy, wfc2, trans_b=True, kind=EPI_DGELU, aux=z)
-        dfc1_b = ops.colsum_bf16(dz)
+        ops.colsum_bf16(dz, out=dfc1_b)
         dfc1_w = _wgrad(dz, v)
         dv = ops.gemm(dz, wfc1, trans_b=True, kind=EPI_F32)
-        dn2w = torch.zeros(C, dtype=torch.float32, device=dev)
-        dn2b = torch.zeros(C, dtype=torch.float32, device=dev)
         dx1 = ops.layernorm_bwd(dv, x1, mean2, rstd2, n2w, dn2w, dn2b, dres=dx2)
         # ---- attention branch ----
-        da, dproj_b = ops.scale_cast_colsum(dx1, drop_a, N)
+        da, _ = ops.scale_cast_colsum(dx1, drop_a, N, colsum_out=dproj_b)
         if ws > 0:
             da = ops.window_partition_bf16(da, Bp, h, w, ws)
             Bw = da.shape[0] // (ws * ws)
@@ -162,13 +166,11 @@ class BlockFn(torch.autograd.Function):
             dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bw, heads, ws, ws)
         else:
             dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bp, heads, h, w)
-        dqkv_b = ops.colsum_bf16(dqkv)
+        ops.colsum_bf16(dqkv, out=dqkv_b)
         dqkv_w = _wgrad(dqkv, u)
         du = ops.gemm(dqkv, wqkv, trans_b=True, kind=EPI_F32)
         if ws > 0:
             du = ops.window_unpartition(du, Bp, h, w, ws)   # gradients at padded tokens are dropped
-        dn1w = torch.zeros(C, dtype=torch.float32, device=dev)
-        dn1b = torch.zeros(C, dtype=torch.float32, device=dev)
         dx = ops.layernorm_bwd(du, x, mean1, rstd1, n1w, dn1w, dn1b, dres=dx1)
         return (dx, None, None, dn1w, dn1b, dTh, dTw, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b,
                 dfc2_w, dfc2_b, None)

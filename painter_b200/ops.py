@@ -239,21 +239,25 @@ def cast_bf16(x):
     return out
 
 
-def scale_cast_colsum(x, rowscale=None, rows_per_group=0, want_colsum=True):
-    """fp32 [M, C] -> (bf16 [M, C] scaled per row group, column sums fp32 [C])."""
+def scale_cast_colsum(x, rowscale=None, rows_per_group=0, want_colsum=True, colsum_out=None):
+    """fp32 [M, C] -> (bf16 [M, C] scaled per row group, column sums fp32 [C]).  colsum_out: pre-zeroed [C] buffer."""
     _req(x, torch.float32, "x")
     M, C = x.shape
     out = torch.empty((M, C), dtype=torch.bfloat16, device=x.device)
-    cs = torch.zeros((C,), dtype=torch.float32, device=x.device) if want_colsum else None
+    if colsum_out is not None:
+        cs = colsum_out
+    else:
+        cs = torch.zeros((C,), dtype=torch.float32, device=x.device) if want_colsum else None
     check(lib().pk_scale_cast_colsum(_ptr(x), x.stride(0), _ptr(rowscale), rows_per_group, _ptr(out), _ptr(cs), M, C,
                                      _stream()), "pk_scale_cast_colsum")
     return out, cs
 
 
-def colsum_bf16(x, ncols=None):
+def colsum_bf16(x, out=None):
+    """Column sums of a bf16 [M, C] matrix, accumulated into `out` (pre-zeroed fp32 [C]) if given."""
     _req(x, torch.bfloat16, "x")
     M, C = x.shape
-    cs = torch.zeros((C,), dtype=torch.float32, device=x.device)
+    cs = out if out is not None else torch.zeros((C,), dtype=torch.float32, device=x.device)
     check(lib().pk_colsum_bf16(_ptr(x), x.stride(0), _ptr(cs), M, C, _stream()), "pk_colsum_bf16")
     return cs
 

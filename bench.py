@@ -158,7 +158,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from painter_b200 import _lib, models_painter, ops
+    from painter_b200 import _lib, dist_utils, models_painter, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -184,7 +184,7 @@ def main():
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, fused=True)
 
-    host = [t.pin_memory() for t in _batch(B, rank)]
+    host = [t.pin_memory() for t in _batch(B, dist_utils.rank_seed(0, rank) % 9973)]
     resident = [t.to(dev) for t in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
@@ -257,10 +257,7 @@ def main():
     ms_e2e = e2.elapsed_time(e3)
     clk = clocks.stop() if rank == 0 else None
 
-    t = torch.tensor([ms_total, ms_e2e], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e = dist_utils.max_over_ranks([ms_total, ms_e2e], device=dev)   # slowest rank
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
     e2e_val = world * B / (ms_e2e / args.steps / 1e3)

@@ -641,6 +641,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         AB_TRACE(1, 0, i, 3);
         tc_fence_after();
         if (i + 1 < num_q) issue_dp(i + 1);
+        AB_TRACE(1, 0, i, 5);
         const uint64_t dQ0 = make_sdesc(sQ0 + qs * 32768, 16, 1024), ddO0 = make_sdesc(sQ0 + qs * 32768 + 16384, 16, 1024);
         const uint64_t dP0 = make_sdesc(sP + (i & 1) * 32768, 16384, 1024), ddS0 = make_sdesc(sdS, 16384, 1024);
         // dK[keys, d] += dS^T . Q first (releases the single dS buffer), then dV[keys, d] += P^T . dO
@@ -671,27 +672,48 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const size_t bh = static_cast<size_t>(b) * a.heads + head;
     const float sc = a.scale_log2;
     const int keys_valid = (h - jt * R) * W - cbase;
-    for (int i = 0; i < num_q; ++i) {
+    // Per-row operands of a query tile (LSE, delta, R/2 rel_h values, W rel_w values) come from global memory:
+    // they are fetched one tile AHEAD into registers so that their latency hides behind the current tile's work.
+    float lse_n = 0.f, delta_n = 0.f, hb_n[RH], relw_n[W];
+    bool valid_n = false;
+    auto fetch = [&](int i) {
       int t = i * AB_BM + row;
-      const bool valid = t < a.N;
-      if (!valid) t = a.N - 1;
-      const float lse = a.lse[bh * a.N + t];
-      const float delta = a.delta[bh * a.N + t];
-      float hb[RH], relw[W];
-      {
-        const float* ph = a.relh_g + (bh * a.N + t) * h;
+      valid_n = t < a.N;
+      if (!valid_n) t = a.N - 1;
+      lse_n = a.lse[bh * a.N + t];
+      delta_n = a.delta[bh * a.N + t];
+      const float* ph = a.relh_g + (bh * a.N + t) * h;
 #pragma unroll
-        for (int r = 0; r < RH; ++r) {
-          const int ii = jt * R + half * RH + r;
-          hb[r] = ph[ii < h ? ii : h - 1] - lse;
-        }
-        const float* pw = a.relw_g + (bh * a.N + t) * W;
-#pragma unroll
-        for (int j = 0; j < W; ++j) relw[j] = pw[j];
+      for (int r = 0; r < RH; ++r) {
+        const int ii = jt * R + half * RH + r;
+        hb_n[r] = ph[ii < h ? ii : h - 1];
       }
+      const float* pw = a.relw_g + (bh * a.N + t) * W;
+      if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) {
+          const float4 q4 = reinterpret_cast<const float4*>(pw)[j];
+          relw_n[4 * j] = q4.x; relw_n[4 * j + 1] = q4.y; relw_n[4 * j + 2] = q4.z; relw_n[4 * j + 3] = q4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) relw_n[j] = pw[j];
+      }
+    };
+    fetch(0);
+    for (int i = 0; i < num_q; ++i) {
+      const bool valid = valid_n;
+      const float lse = lse_n, delta = delta_n;
+      float hb[RH], relw[W];
+#pragma unroll
+      for (int r = 0; r < RH; ++r) hb[r] = hb_n[r] - lse;
+#pragma unroll
+      for (int j = 0; j < W; ++j) relw[j] = relw_n[j];
+      if (i + 1 < num_q) fetch(i + 1);
       const bool full = keys_valid >= AB_KT / 2 && valid;
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 0);
       mbar_wait(bar_s + 8 * (i & 1), (i >> 1) & 1);
+      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 4);
       mbar_wait(bar_dp, i & 1);
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 1);
       tc_fence_after();

@@ -41,7 +41,7 @@ t2 = buf2.cpu().view(2, 2, 16, 8)
 for kern, kn in ((0, "dq "), (1, "dkv")):
     t0 = int(t2[kern, 0, 0, 0])
     for j in range(14 if kern == 0 else 13):
-        m = [int(t2[kern, 0, j, e]) - t0 for e in range(5)]
-        sx = [int(t2[kern, 1, j, e]) - t0 for e in range(4)]
-        print(f"{kn} it {j:2d}: mma top={m[0]:7d} ld_seen={m[1]:7d} sdp_issued={m[2]:7d} p_seen={m[3]:7d} "
-              f"acc_issued={m[4]:7d} | smx wait={sx[0]:7d} s_seen={sx[1]:7d} done={sx[2]:7d} arrived={sx[3]:7d}")
+        m = [int(t2[kern, 0, j, e]) - t0 for e in range(6)]
+        sx = [int(t2[kern, 1, j, e]) - t0 for e in range(5)]
+        print(f"{kn} it {j:2d}: mma top={m[0]:7d} s_next_issued={m[2]:7d} p_seen={m[3]:7d} dp_next_issued={m[5]:7d} "
+              f"acc_issued={m[4]:7d} | smx wait={sx[0]:7d} bar_s_seen={sx[4]:7d} bar_dp_seen={sx[1]:7d} done={sx[2]:7d} arrived={sx[3]:7d}")

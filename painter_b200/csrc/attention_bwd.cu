@@ -88,7 +88,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t bar0 = base + srelh_off + a.relh_bytes;
   const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*3*/, bar_ke = bar0 + 32 /*3*/, bar_s = bar0 + 56 /*2*/,
                  bar_p = bar0 + 72, bar_g = bar0 + 80, bar_gr = bar0 + 88, bar_e = bar0 + 96,
-                 bar_er = bar0 + 104, bar_t = bar0 + 112;
+                 bar_er = bar0 + 104, bar_t = bar0 + 112,
+                 bar_gw = bar0 + 128;  // G_w retired (single completion; bar_g completes twice and would alias)
   const uint32_t holder = bar0 + 120;
   volatile uint32_t* holder_gen =
       reinterpret_cast<volatile uint32_t*>(gen + srelh_off + a.relh_bytes + 120);
@@ -117,6 +118,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_e, 1);
     mbar_init(bar_er, AB_SMX);
     mbar_init(bar_t, 1);
+    mbar_init(bar_gw, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(holder, 512);
@@ -138,7 +140,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = 0; j < num_tiles; ++j) {
         const int st = j % KS;
         if (j >= KS) mbar_wait(bar_ke + 8 * st, ((j / KS) - 1) & 1);
-        if (j == KS - 1) mbar_wait(bar_g, 0);  // G_w MMA done with T_w (last stage's V buffer)
+        if (j == KS - 1) mbar_wait(bar_gw, 0);  // G_w MMA done with T_w (last stage's V buffer)
         mbar_expect_tx(bar_kf + 8 * st, 2 * AB_KT * 128);
         tma_load_3d(sKV + st * 28672, &tmKV, bar_kf + 8 * st, C + head * 64, j * AB_KT, b);
         tma_load_3d(sKV + st * 28672 + 14336, &tmKV, bar_kf + 8 * st, 2 * C + head * 64, j * AB_KT, b);
@@ -163,6 +165,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int k = 0; k < 4; ++k)
             umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sT + k * 32, 16, 1024), idesc, k != 0);
           umma_commit(bar_g);
+          umma_commit(bar_gw);
         }
         __syncwarp();
       }

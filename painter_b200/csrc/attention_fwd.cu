@@ -69,7 +69,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t bar0 = base + ATT_SRELH + a.relh_bytes;
   const uint32_t bar_q = bar0, bar_kf = bar0 + 8, bar_ke = bar0 + 16, bar_vf = bar0 + 24,
                  bar_ve = bar0 + 32, bar_s = bar0 + 40, bar_p = bar0 + 48, bar_o = bar0 + 56,
-                 bar_g = bar0 + 64, bar_gr = bar0 + 72;
+                 bar_g = bar0 + 64, bar_gr = bar0 + 72,
+                 bar_gw = bar0 + 88;  // G_w retired (single completion: the producer must not alias bar_g's phases)
   const uint32_t holder = bar0 + 80;
   volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + ATT_SRELH + a.relh_bytes + 80);
 
@@ -94,6 +95,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(bar_o, 1);
     mbar_init(bar_g, 1);
     mbar_init(bar_gr, 128);
+    mbar_init(bar_gw, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(holder, 256);
@@ -112,7 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_2d(sV, &tmTw, bar_q, 0, 0);
       mbar_expect_tx(bar_kf, ATT_KT * 128);
       tma_load_3d(sK, &tmKV, bar_kf, C + head * 64, 0, b);
-      mbar_wait(bar_g, 0);  // G_w MMA finished reading T_w out of the V buffer
+      mbar_wait(bar_gw, 0);  // G_w MMA finished reading T_w out of the V buffer
       mbar_expect_tx(bar_vf, ATT_KT * 128);
       tma_load_3d(sV, &tmKV, bar_vf, 2 * C + head * 64, 0, b);
       for (int j = 1; j < num_tiles; ++j) {
@@ -139,6 +141,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int k = 0; k < 4; ++k)
             umma_ss(tS, make_sdesc(sQ + k * 32, 16, 1024), make_sdesc(sV + k * 32, 16, 1024), idesc, k != 0);
           umma_commit(bar_g);
+          umma_commit(bar_gw);
         }
         __syncwarp();
       }

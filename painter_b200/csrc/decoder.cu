@@ -125,45 +125,114 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ c1, const float* __restrict__ 
   const size_t plane = static_cast<size_t>(H) * W;
   const size_t npix = static_cast<size_t>(B) * plane;
   float dga0 = 0, dga1 = 0, dbe0 = 0, dbe1 = 0, dw0[3] = {0, 0, 0}, dw1[3] = {0, 0, 0}, db1[3] = {0, 0, 0};
-  for (size_t pix = gw; pix < npix; pix += warps_total) {
-    const int b = static_cast<int>(pix / plane);
-    const size_t yx = pix % plane;
-    const int y = static_cast<int>(yx / W), x = static_cast<int>(yx % W);
-    const uint32_t u = reinterpret_cast<const uint32_t*>(c1)[pix * 32 + lane];
-    const float x0 = __uint_as_float(u << 16), x1 = __uint_as_float(u & 0xFFFF0000u);
-    const float mean = warp_sum(x0 + x1) * (1.f / 64);
-    const float d0 = x0 - mean, d1 = x1 - mean;
-    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64) + 1e-6f);
-    const float xh0 = d0 * rstd, xh1 = d1 * rstd;
-    const float ln0 = ga0 * xh0 + be0, ln1 = ga1 * xh1 + be1;
-    const float ge0 = gelu_erf(ln0), ge1 = gelu_erf(ln1);
-    const float m = mask[static_cast<size_t>(b % maskB) * Ntok + (y / p) * wt + x / p] ? 1.f : 0.f;
-    float dg0 = 0.f, dg1 = 0.f;
+  // PP pixels per warp iteration: the seven shuffle reductions of a pixel form one long dependent chain, so
+  // several independent pixels are interleaved to keep the issue slots busy.
+  constexpr int PP = 4;
+  // 32-bit index math (npix < 2^31 is checked on the host); W % PP == 0 keeps the PP pixels in one row, so the
+  // divisions happen once per group.
+  const uint32_t npix32 = static_cast<uint32_t>(npix), plane32 = static_cast<uint32_t>(plane);
+  for (uint32_t pix0 = static_cast<uint32_t>(gw) * PP; pix0 < npix32; pix0 += static_cast<uint32_t>(warps_total) * PP) {
+    float x0[PP], x1[PP], mean[PP], rstd[PP], xh0[PP], xh1[PP], ln0[PP], ln1[PP], ge0[PP], ge1[PP], mk[PP];
+    float dg0[PP], dg1[PP];
+    uint32_t yx[PP];
+    uint32_t raw[PP];
+    constexpr bool live[PP] = {true, true, true, true};
+    const uint32_t bq = pix0 / plane32, yx0 = pix0 - bq * plane32;
+    const uint32_t yq = yx0 / static_cast<uint32_t>(W), xq = yx0 - yq * static_cast<uint32_t>(W);
+    const uint8_t* mrow = mask + static_cast<size_t>(bq % maskB) * Ntok + (yq / p) * wt;
+    const int bb[PP] = {static_cast<int>(bq), static_cast<int>(bq), static_cast<int>(bq), static_cast<int>(bq)};
+#pragma unroll
+    for (int u = 0; u < PP; ++u) {
+      yx[u] = yx0 + u;
+      raw[u] = reinterpret_cast<const uint32_t*>(c1)[static_cast<size_t>(pix0 + u) * 32 + lane];
+    }
+#pragma unroll
+    for (int u = 0; u < PP; ++u) {
+      x0[u] = __uint_as_float(raw[u] << 16);
+      x1[u] = __uint_as_float(raw[u] & 0xFFFF0000u);
+      mk[u] = mrow[(xq + u) / p] ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < PP; ++u) mean[u] = x0[u] + x1[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < PP; ++u) mean[u] += __shfl_xor_sync(0xffffffffu, mean[u], o);
+#pragma unroll
+    for (int u = 0; u < PP; ++u) {
+      mean[u] *= (1.f / 64);
+      const float d0 = x0[u] - mean[u], d1 = x1[u] - mean[u];
+      xh0[u] = d0;
+      xh1[u] = d1;
+      rstd[u] = d0 * d0 + d1 * d1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < PP; ++u) rstd[u] += __shfl_xor_sync(0xffffffffu, rstd[u], o);
+#pragma unroll
+    for (int u = 0; u < PP; ++u) {
+      rstd[u] = rsqrtf(rstd[u] * (1.f / 64) + 1e-6f);
+      xh0[u] *= rstd[u];
+      xh1[u] *= rstd[u];
+      ln0[u] = ga0 * xh0[u] + be0;
+      ln1[u] = ga1 * xh1[u] + be1;
+      ge0[u] = gelu_erf(ln0[u]);
+      ge1[u] = gelu_erf(ln1[u]);
+      dg0[u] = 0.f;
+      dg1[u] = 0.f;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float pred = warp_sum(w0[c] * ge0 + w1[c] * ge1) + b1[c];
-      const size_t o = (static_cast<size_t>(b) * 3 + c) * plane + yx;
-      const float d = pred - tgts[o];
-      float dl;
-      if (loss_kind == 0) dl = fminf(fmaxf(d * 100.f, -1.f), 1.f);
-      else if (loss_kind == 1) dl = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-      else if (loss_kind == 2) dl = 2.f * d;
-      else dl = 0.5f * ((d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + 2.f * d);
-      const float dp = gs * coef[b] * m * valid[o] * dl;
-      dw0[c] += dp * ge0;
-      dw1[c] += dp * ge1;
-      db1[c] += dp;
-      dg0 += dp * w0[c];
-      dg1 += dp * w1[c];
+      float pr[PP];
+#pragma unroll
+      for (int u = 0; u < PP; ++u) pr[u] = w0[c] * ge0[u] + w1[c] * ge1[u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < PP; ++u) pr[u] += __shfl_xor_sync(0xffffffffu, pr[u], o);
+#pragma unroll
+      for (int u = 0; u < PP; ++u) {
+        const size_t o = (static_cast<size_t>(bb[u]) * 3 + c) * plane + yx[u];
+        const float d = pr[u] + b1[c] - tgts[o];
+        float dl;
+        if (loss_kind == 0) dl = fminf(fmaxf(d * 100.f, -1.f), 1.f);
+        else if (loss_kind == 1) dl = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        else if (loss_kind == 2) dl = 2.f * d;
+        else dl = 0.5f * ((d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + 2.f * d);
+        const float dp = live[u] ? gs * coef[bb[u]] * mk[u] * valid[o] * dl : 0.f;
+        dw0[c] += dp * ge0[u];
+        dw1[c] += dp * ge1[u];
+        db1[c] += dp;
+        dg0[u] += dp * w0[c];
+        dg1[u] += dp * w1[c];
+      }
     }
-    const float dln0 = dg0 * gelu_erf_grad(ln0), dln1 = dg1 * gelu_erf_grad(ln1);
-    dga0 += dln0 * xh0; dga1 += dln1 * xh1;
-    dbe0 += dln0; dbe1 += dln1;
-    const float dx0 = dln0 * ga0, dx1 = dln1 * ga1;
-    const float c1m = warp_sum(dx0 + dx1) * (1.f / 64);
-    const float c2m = warp_sum(dx0 * xh0 + dx1 * xh1) * (1.f / 64);
-    const float o0 = rstd * (dx0 - c1m - xh0 * c2m), o1 = rstd * (dx1 - c1m - xh1 * c2m);
-    reinterpret_cast<uint32_t*>(dc1)[pix * 32 + lane] = pack_bf16x2(o0, o1);
+    float dx0[PP], dx1[PP], c1m[PP], c2m[PP];
+#pragma unroll
+    for (int u = 0; u < PP; ++u) {
+      const float dln0 = dg0[u] * gelu_erf_grad(ln0[u]), dln1 = dg1[u] * gelu_erf_grad(ln1[u]);
+      dga0 += dln0 * xh0[u]; dga1 += dln1 * xh1[u];
+      dbe0 += dln0; dbe1 += dln1;
+      dx0[u] = dln0 * ga0;
+      dx1[u] = dln1 * ga1;
+      c1m[u] = dx0[u] + dx1[u];
+      c2m[u] = dx0[u] * xh0[u] + dx1[u] * xh1[u];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < PP; ++u) {
+        c1m[u] += __shfl_xor_sync(0xffffffffu, c1m[u], o);
+        c2m[u] += __shfl_xor_sync(0xffffffffu, c2m[u], o);
+      }
+#pragma unroll
+    for (int u = 0; u < PP; ++u) {
+      if (!live[u]) continue;
+      const float a1 = c1m[u] * (1.f / 64), a2 = c2m[u] * (1.f / 64);
+      const float o0 = rstd[u] * (dx0[u] - a1 - xh0[u] * a2), o1 = rstd[u] * (dx1[u] - a1 - xh1[u] * a2);
+      reinterpret_cast<uint32_t*>(dc1)[static_cast<size_t>(pix0 + u) * 32 + lane] = pack_bf16x2(o0, o1);
+    }
   }
   // block reduction through shared memory, then atomics
   __shared__ float red[8][323];
@@ -227,7 +296,9 @@ extern "C" int pk_decoder_head_bwd(const void* c1, const float* tgts, const uint
                                    int H, int W, int p, int loss_kind, void* stream) {
   PK_CHECK(c1 && tgts && mask && valid && coef && head_params && dc1 && dhead_params_zeroed,
            "pk_decoder_head_bwd: null pointer");
-  const int grid = sm_count() * 8;
+  PK_CHECK(W % 4 == 0 && static_cast<long long>(B) * H * W < (1ll << 31),
+           "pk_decoder_head_bwd: W must be a multiple of 4 and B*H*W < 2^31");
+  const int grid = sm_count() * 4;
   head_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(c1), tgts, mask, maskB, valid, coef, gscale, head_params,
       static_cast<__nv_bfloat16*>(dc1), dhead_params_zeroed, B, H, W, p, loss_kind);

@@ -53,28 +53,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int total_tiles = tiles_mn * g.splits;
   const uint32_t tmem_cols = 2u * BN;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 6) tmem_alloc(holder, tmem_cols);
+  if (warp == 10) tmem_alloc(holder, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_gen;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ------------------------------ TMA producer ------------------------------
       uint32_t s = 0, ph = 0;
@@ -127,7 +127,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     {
       // ------------------------------- MMA issuer -------------------------------
       // warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues tcgen05
@@ -166,9 +166,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < GEMM_EPI_WARPS) {
     // --------------------------------- epilogue ---------------------------------
-    const int ew = warp;
+    const int ew = warp & 3;   // TMEM lane quarter
+    const int eg = warp >> 2;  // column group: this warp owns the 64-column blocks with (c0 / 64) % 2 == eg
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mn = tile % tiles_mn;
@@ -180,7 +181,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m_blk * GEMM_BM + rloc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       if constexpr (KIND == EPI_HEAD || KIND == EPI_UNSHUF) {
-        // pixel-row tile: rloc -> (b, y, x)
+        // pixel-row tile (64 columns: handled by column group 0; group 1 only signals): rloc -> (b, y, x)
+        if (eg == 0) {
         const int tx = m_blk % g.conv.tiles_x, r1 = m_blk / g.conv.tiles_x;
         const int ty = r1 % g.conv.tiles_y, bi = r1 / g.conv.tiles_y;
         const int y = ty * g.conv.TH + rloc / g.conv.TW, x = tx * g.conv.TW + rloc % g.conv.TW;
@@ -210,19 +212,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             store_bf16x32(dst + c0, xv);
           }
         }
+        }
       } else {
-        float* stg = stg_gen + ew * (32 * STG_LD);
+        float* stg = stg_gen + warp * (32 * STG_LD);
         const int row0 = m_blk * GEMM_BM + ew * 32;
         EpiAux auxA, auxB;   // explicit ping-pong (BN is a multiple of 64): keeps both in registers
-        gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN, auxA);
-        for (int c0 = 0; c0 < BN; c0 += 64) {
+        if (eg * 64 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + eg * 64, auxA);
+        for (int c0 = eg * 64; c0 < BN; c0 += 128) {
           uint32_t v[32];
           tmem_ld_x32(taddr + c0, v);
           gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 32, auxB);
           tmem_wait_ld();
           gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, v, auxA);
           tmem_ld_x32(taddr + c0 + 32, v);
-          if (c0 + 64 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 64, auxA);
+          if (c0 + 128 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 128, auxA);
           tmem_wait_ld();
           gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0 + 32, v, auxB);
         }
@@ -236,7 +239,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 6) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 10) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 int g_force_bn = 0;
@@ -248,7 +251,7 @@ int launch_gemm2(const void* A, const void* B, int lda, int ldb, GemmArgs& g, cu
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs& g, cudaStream_t st,
                        const char* who) {
   const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + g.BN * 128) + 256 +
-                      4 * 32 * STG_LD * sizeof(float);
+                      GEMM_EPI_WARPS * 32 * STG_LD * sizeof(float);
   const int total = g.num_m_tiles * g.num_n_tiles * g.splits;
   const int sms = sm_count();
   const int grid = total < sms ? total : sms;
@@ -343,7 +346,7 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
   }
   if (g_force_bn > 0 && N % g_force_bn == 0) BN = g_force_bn;
   g.BN = BN;
-  g.stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  g.stages = gemm_stages_for(GEMM_A_BYTES + BN * 128);
   g.num_m_tiles = mt;
   g.num_n_tiles = N / BN;
   // split-K: only for plain fp32 outputs whose tile count cannot fill the machine (wgrad GEMMs);
@@ -366,7 +369,7 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
   if (g_use_2cta && (BN == 256 || BN == 128) && M >= 256) {
     GemmArgs g2 = g;
     g2.num_m_tiles = (M + 255) / 256;
-    g2.stages = BN == 256 ? 6 : 8;
+    g2.stages = gemm_stages_for(GEMM_A_BYTES + (BN / 2) * 128);
     if (g2.epi.kind == PK_EPI_F32 && epi->accumulate == 2) {
       g2.epi.accumulate = 2;
       int want = (sms / 2) / (g2.num_m_tiles * g2.num_n_tiles);
@@ -414,7 +417,7 @@ static int conv_common(const void* img_nhwc, const void* wmat, int B, int H, int
   g.N = 64;
   g.K = 576;
   g.BN = 64;
-  g.stages = 8;
+  g.stages = gemm_stages_for(GEMM_A_BYTES + 64 * 128);
   g.transA = g.transB = 0;
   g.splits = 1;
   g.kb_per_split = 9;
@@ -481,7 +484,7 @@ extern "C" int pk_conv3x3_wgrad(const void* g_nhwc, const void* dc1_nhwc, float*
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = 576; g.N = 64; g.K = B * H * W;
-  g.BN = 64; g.stages = 8;
+  g.BN = 64; g.stages = gemm_stages_for(GEMM_A_BYTES + 64 * 128);
   g.transA = g.transB = 1;
   g.conv.mode = 2;
   g.conv.H = H; g.conv.W = W; g.conv.TW = TW; g.conv.TH = TH;

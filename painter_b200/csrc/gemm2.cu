@@ -99,28 +99,28 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_cols = 2u * BN;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is waited on)
+      mbar_init(tempty_bar(s), 2 * GEMM_EPI_WARPS);  // epilogue warps of both CTAs (only the leader's copy is waited on)
     }
     fence_barrier_init();
   }
-  if (warp == 6) tmem_alloc2(holder, tmem_cols);
+  if (warp == 10) tmem_alloc2(holder, tmem_cols);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *holder_gen;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ------------------------------ TMA producer (both CTAs) ------------------------------
       uint32_t s = 0, ph = 0;
@@ -156,7 +156,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (leader) {
       // ------------------------------- MMA issuer (leader CTA) -------------------------------
       const uint32_t idesc = make_idesc_bf16(256, BN, g.transA != 0, g.transB != 0);
@@ -194,11 +194,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < GEMM_EPI_WARPS) {
     // --------------------------------- epilogue (both CTAs) ---------------------------------
-    const int ew = warp;
+    const int ew = warp & 3;   // TMEM lane quarter
+    const int eg = warp >> 2;  // column group: this warp owns the 64-column blocks with (c0 / 64) % 2 == eg
     uint32_t it = 0;
-    float* stg = stg_gen + ew * (32 * STG_LD);
+    float* stg = stg_gen + warp * (32 * STG_LD);
     for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
       const int mn = tile % tiles_mn;
       const int m_blk = mn % g.num_m_tiles, n_blk = mn / g.num_m_tiles;
@@ -208,15 +209,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + ew * 32;
       EpiAux auxA, auxB;   // explicit ping-pong (BN is a multiple of 64): keeps both in registers
-      gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN, auxA);
-      for (int c0 = 0; c0 < BN; c0 += 64) {
+      if (eg * 64 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + eg * 64, auxA);
+      for (int c0 = eg * 64; c0 < BN; c0 += 128) {
         uint32_t v[32];
         tmem_ld_x32(taddr + c0, v);
         gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 32, auxB);
         tmem_wait_ld();
         gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, v, auxA);
         tmem_ld_x32(taddr + c0 + 32, v);
-        if (c0 + 64 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 64, auxA);
+        if (c0 + 128 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 128, auxA);
         tmem_wait_ld();
         gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0 + 32, v, auxB);
       }
@@ -229,7 +230,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  if (warp == 6) tmem_dealloc2(tmem_base, tmem_cols);
+  if (warp == 10) tmem_dealloc2(tmem_base, tmem_cols);
 }
 
 // Launcher used by pk_gemm_bf16 (gemm.cu).  g.BN / g.stages / g.num_*_tiles are already in pair units.
@@ -253,7 +254,7 @@ int launch_gemm2(const void* A, const void* B, int lda, int ldb, GemmArgs& g, cu
   if (!make_tmap_bf16(&tmB, B, 2, dims, strides, box)) return 3;
 
   const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + (g.BN / 2) * 128) + 256 +
-                      4 * 32 * STG_LD * sizeof(float);
+                      GEMM_EPI_WARPS * 32 * STG_LD * sizeof(float);
   const int total = g.num_m_tiles * g.num_n_tiles * g.splits;
   int clusters = sm_count() / 2;
   if (clusters > total) clusters = total;

@@ -12,7 +12,8 @@ namespace pk {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KiB
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 352;   // 8 epilogue warps + TMA warp + MMA warp + TMEM-allocator warp
+constexpr int GEMM_EPI_WARPS = 8;
 
 // internal epilogue kinds (beyond the public PK_EPI_*)
 constexpr int EPI_HEAD = 100;    // decoder head fused behind the 3x3 conv (LN2D + GELU + 1x1 conv + loss)
@@ -36,6 +37,13 @@ struct HeadArgs {
   float* num;               // [B] atomics: sum smoothl1 * mask * valid
   int maskB, p, loss_kind;
 };
+
+// operand ring depth that fits beside the 8 epilogue staging tiles
+__host__ inline int gemm_stages_for(int stage_bytes) {
+  const int budget = 227 * 1024 - 1024 - 256 - GEMM_EPI_WARPS * 32 * 36 * 4;
+  int st = budget / stage_bytes;
+  return st > 8 ? 8 : st;
+}
 
 struct GemmArgs {
   int M, N, K;

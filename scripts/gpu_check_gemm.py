@@ -37,6 +37,11 @@ CASES += [
     ("tt_wgrad_fc1", 4096, 1024, 12544, 1, 1, "f32", 0),
     ("tt_wgrad_qkv", 3072, 1024, 12544, 1, 1, "f32", 0),
     ("nt_seggpt_qkv", 3136, 3072, 1024, 0, 0, "bf16", 0),
+    # operand-major study at the wgrad shape (K = tokens)
+    ("mj_nt", 4096, 1024, 12544, 0, 0, "f32", 0),
+    ("mj_tn", 4096, 1024, 12544, 1, 0, "f32", 0),
+    ("mj_nn", 4096, 1024, 12544, 0, 1, "f32", 0),
+    ("mj_tt", 4096, 1024, 12544, 1, 1, "f32", 0),
 ]
 
 

@@ -371,14 +371,26 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
     g2.num_m_tiles = (M + 255) / 256;
     g2.stages = gemm_stages_for(GEMM_A_BYTES + (BN / 2) * 128);
     if (g2.epi.kind == PK_EPI_F32 && epi->accumulate == 2) {
+      // zero-initialised fp32 output (weight gradients): stream-K.  The tiles_mn * num_kb k-block units are cut
+      // into one equal range per cluster; a tile that straddles ranges is finished with fp32 atomics.
       g2.epi.accumulate = 2;
-      int want = (sms / 2) / (g2.num_m_tiles * g2.num_n_tiles);
-      if (want < 1) want = 1;
-      if (want > num_kb / 8) want = num_kb / 8 > 0 ? num_kb / 8 : 1;
-      if (g_force_splits > 0) want = g_force_splits < num_kb ? g_force_splits : num_kb;
-      g2.kb_per_split = (num_kb + want - 1) / want;
-      g2.splits = (num_kb + g2.kb_per_split - 1) / g2.kb_per_split;
-      if (g2.splits == 1) g2.epi.accumulate = 1;
+      g2.splits = 1;
+      g2.kb_per_split = num_kb;
+      const int clusters = sms / 2;
+      const int tiles2 = g2.num_m_tiles * g2.num_n_tiles;
+      const long long units = static_cast<long long>(tiles2) * num_kb;
+      if (g_force_splits > 0) {
+        const int want = g_force_splits < num_kb ? g_force_splits : num_kb;
+        g2.kb_per_split = (num_kb + want - 1) / want;
+        g2.splits = (num_kb + g2.kb_per_split - 1) / g2.kb_per_split;
+        if (g2.splits == 1) g2.epi.accumulate = 1;
+      } else if (tiles2 % clusters == 0 || units < 4ll * clusters) {
+        g2.epi.accumulate = 1;   // already balanced (or too small to matter): plain data-parallel tiles
+      } else {
+        int per = static_cast<int>((units + clusters - 1) / clusters);
+        if (per < 4) per = 4;
+        g2.streamk_units = per;
+      }
     }
     return launch_gemm2(A, B, lda, ldb, g2, static_cast<cudaStream_t>(stream));
   }

@@ -95,7 +95,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool leader = rank == 0;
   const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
   const int tiles_mn = g.num_m_tiles * g.num_n_tiles;   // m tiles are 256 rows here
-  const int total_tiles = tiles_mn * g.splits;
   const uint32_t tmem_cols = 2u * BN;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
@@ -124,11 +123,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       // ------------------------------ TMA producer (both CTAs) ------------------------------
       uint32_t s = 0, ph = 0;
-      for (int tile = cid; tile < total_tiles; tile += ncl) {
-        const int mn = tile % tiles_mn, split = tile / tiles_mn;
+      GemmSched sch;
+      sch.init(g, tiles_mn, num_kb, cid, ncl);
+      int mn, kb0, kb1;
+      while (sch.next(mn, kb0, kb1)) {
         const int m_blk = mn % g.num_m_tiles, n_blk = mn / g.num_m_tiles;
-        const int kb0 = split * g.kb_per_split;
-        const int kb1 = min(num_kb, kb0 + g.kb_per_split);
         const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
         const int n0 = n_blk * BN + static_cast<int>(rank) * BNh;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -161,14 +160,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ------------------------------- MMA issuer (leader CTA) -------------------------------
       const uint32_t idesc = make_idesc_bf16(256, BN, g.transA != 0, g.transB != 0);
       uint32_t s = 0, ph = 0, it = 0;
-      for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
+      GemmSched sch;
+      sch.init(g, tiles_mn, num_kb, cid, ncl);
+      int mn, kb0, kb1;
+      for (; sch.next(mn, kb0, kb1); ++it) {
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        const int split = tile / tiles_mn;
-        const int kb0 = split * g.kb_per_split;
-        const int kb1 = min(num_kb, kb0 + g.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
@@ -200,8 +199,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int eg = warp >> 2;  // column group: this warp owns the 64-column blocks with (c0 / 64) % 2 == eg
     uint32_t it = 0;
     float* stg = stg_gen + warp * (32 * STG_LD);
-    for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
-      const int mn = tile % tiles_mn;
+    GemmSched sch;
+    sch.init(g, tiles_mn, num_kb, cid, ncl);
+    int mn, kb0, kb1;
+    for (; sch.next(mn, kb0, kb1); ++it) {
       const int m_blk = mn % g.num_m_tiles, n_blk = mn / g.num_m_tiles;
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       mbar_wait(tfull_bar(as), aph);
@@ -257,7 +258,12 @@ int launch_gemm2(const void* A, const void* B, int lda, int ldb, GemmArgs& g, cu
                       GEMM_EPI_WARPS * 32 * STG_LD * sizeof(float);
   const int total = g.num_m_tiles * g.num_n_tiles * g.splits;
   int clusters = sm_count() / 2;
-  if (clusters > total) clusters = total;
+  if (g.streamk_units > 0) {
+    const int units = g.num_m_tiles * g.num_n_tiles * ((g.K + GEMM_BK - 1) / GEMM_BK);
+    clusters = (units + g.streamk_units - 1) / g.streamk_units;
+  } else if (clusters > total) {
+    clusters = total;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);

@@ -52,9 +52,53 @@ struct GemmArgs {
   int transA, transB;
   int num_m_tiles, num_n_tiles;
   int splits, kb_per_split;  // split-K (epilogue accumulates with fp32 atomics when splits > 1)
+  int streamk_units;         // > 0: stream-K (2-CTA kernel): every cluster owns this many consecutive
+                             // (tile, k-block) units; partial tiles are added with fp32 atomics
   PkEpilogue epi;
   ConvArgs conv;
   HeadArgs head;
+};
+
+// Work iterator shared by the producer / MMA / epilogue roles of the persistent kernels: each role walks the same
+// sequence of (output tile, k-block range) items.  Classic mode: item = (tile, split) strided over the clusters;
+// stream-K mode: the tiles_mn * num_kb k-block units are cut into equal consecutive ranges, one per cluster, so the
+// machine is full whatever the tile count (weight-gradient GEMMs have 16..64 tiles for 74 clusters).
+struct GemmSched {
+  int tiles_mn, num_kb, kbps, total, ncl, cur, end;
+  bool sk;
+  __device__ __forceinline__ void init(const GemmArgs& g, int tiles_mn_, int num_kb_, int cid, int ncl_) {
+    tiles_mn = tiles_mn_;
+    num_kb = num_kb_;
+    kbps = g.kb_per_split;
+    ncl = ncl_;
+    sk = g.streamk_units > 0;
+    if (sk) {
+      total = tiles_mn * num_kb;
+      cur = cid * g.streamk_units;
+      end = min(total, cur + g.streamk_units);
+    } else {
+      total = tiles_mn * g.splits;
+      cur = cid;
+      end = total;
+    }
+  }
+  __device__ __forceinline__ bool next(int& mn, int& kb0, int& kb1) {
+    if (cur >= end) return false;
+    if (sk) {
+      mn = cur / num_kb;
+      kb0 = cur - mn * num_kb;
+      const int len = min(num_kb - kb0, end - cur);
+      kb1 = kb0 + len;
+      cur += len;
+    } else {
+      mn = cur % tiles_mn;
+      const int split = cur / tiles_mn;
+      kb0 = split * kbps;
+      kb1 = min(num_kb, kb0 + kbps);
+      cur += ncl;
+    }
+    return true;
+  }
 };
 
 // decoder-head parameters, refreshed per call by async D2D copies:

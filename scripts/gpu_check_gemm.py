@@ -42,6 +42,12 @@ CASES += [
     ("mj_tn", 4096, 1024, 12544, 1, 0, "f32", 0),
     ("mj_nn", 4096, 1024, 12544, 0, 1, "f32", 0),
     ("mj_tt", 4096, 1024, 12544, 1, 1, "f32", 0),
+    # weight-gradient GEMMs as the engine issues them (zero-initialised output, accumulate=2 -> stream-K)
+    ("sk_fc1", 4096, 1024, 12544, 1, 1, "f32sk", 0),
+    ("sk_fc2", 1024, 4096, 12544, 1, 1, "f32sk", 0),
+    ("sk_qkv", 3072, 1024, 12544, 1, 1, "f32sk", 0),
+    ("sk_proj", 1024, 1024, 12544, 1, 1, "f32sk", 0),
+    ("sk_nt_fc1", 4096, 1024, 12544, 0, 0, "f32sk", 0),
 ]
 
 
@@ -65,6 +71,13 @@ def run_case(name, M, N, K, ta, tb, kind, bn):
     elif kind == "f32":
         fn = lambda: ops.gemm(a_in, b_in, trans_a=ta, trans_b=tb, kind=ops.EPI_F32, alpha=0.5)
         want = ref * 0.5
+    elif kind == "f32sk":
+        acc = torch.zeros(M, N, device=dev)
+        calls = [0]
+        def fn():
+            calls[0] += 1
+            return ops.gemm(a_in, b_in, trans_a=ta, trans_b=tb, kind=ops.EPI_F32, out=acc, accumulate=2)
+        want = ref
     elif kind == "f32acc":
         base = torch.randn(M, N, device=dev)
         def fn():

@@ -53,6 +53,23 @@ def test_gemm_split_k_matches_single_pass():
         assert relmax(out, ref) < 2e-5, s
 
 
+@pytest.mark.parametrize("M,N,K,ta,tb", [(768, 512, 4096, True, True), (1024, 1024, 1568, True, True),
+                                          (3072, 1024, 3136, True, True), (512, 256, 640, False, False),
+                                          (4096, 1024, 1000, True, True)])
+def test_gemm_stream_k_weight_gradient_tiling(M, N, K, ta, tb):
+    """Zero-initialised fp32 outputs (accumulate=2) take the stream-K schedule of the CTA-pair kernel: every cluster
+    owns an equal range of (tile, k-block) units, tiles that straddle ranges are completed with atomics."""
+    from painter_b200 import ops
+    a = (torch.randn((K, M) if ta else (M, K), device=DEV) * 0.5).bfloat16()
+    b = (torch.randn((K, N) if tb else (N, K), device=DEV) * 0.5).bfloat16()
+    ref = (a.float().t() if ta else a.float()) @ (b.float() if tb else b.float().t())
+    out = torch.zeros(M, N, device=DEV)
+    ops.gemm(a, b, trans_a=ta, trans_b=tb, kind=ops.EPI_F32, out=out, accumulate=2)
+    assert relmax(out, ref) < 2e-5
+    ops.gemm(a, b, trans_a=ta, trans_b=tb, kind=ops.EPI_F32, out=out, accumulate=2)   # second pass adds
+    assert relmax(out, 2 * ref) < 2e-5
+
+
 def test_gemm_epilogues():
     from painter_b200 import ops
     M, N, K = 384, 512, 256

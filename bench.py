@@ -203,7 +203,8 @@ def main():
         M = a.shape[1] if kw.get("trans_a") else a.shape[0]
         K = a.shape[0] if kw.get("trans_a") else a.shape[1]
         N = b.shape[1] if kw.get("trans_b") else b.shape[0]
-        gemm_log.append((2.0 * M * N * K, e0, e1))
+        gemm_log.append((2.0 * M * N * K, e0, e1, (M, N, K, int(bool(kw.get("trans_a"))),
+                                                   int(bool(kw.get("trans_b"))), kw.get("kind", 0))))
         return out
 
     ops.gemm = timed_gemm
@@ -263,8 +264,18 @@ def main():
     e2e_val = world * B / (ms_e2e / args.steps / 1e3)
 
     if rank == 0:
-        flops = sum(f for f, _, _ in gemm_log)
-        gms = sum(a.elapsed_time(b) for _, a, b in gemm_log)
+        flops = sum(g[0] for g in gemm_log)
+        gms = sum(g[1].elapsed_time(g[2]) for g in gemm_log)
+        if os.environ.get("PK_BENCH_DETAIL"):      # per-shape GEMM table on stderr (diagnostics only)
+            agg = {}
+            for f, a, b, key in gemm_log:
+                t = agg.setdefault(key, [0, 0.0, 0.0])
+                t[0] += 1
+                t[1] += a.elapsed_time(b)
+                t[2] += f
+            for key, (n, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                print(f"[gemm] M,N,K,tA,tB,kind={key} n/step={n / args.steps:.0f} ms/step={t / args.steps:.3f} "
+                      f"TF/s={f / t / 1e9:.0f}", file=sys.stderr)
         peak, peak_src = _peaks()
         achieved = flops / (gms / 1e3) / 1e12 if gms > 0 else 0.0
         line = {

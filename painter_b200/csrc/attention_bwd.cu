@@ -55,8 +55,7 @@ struct AttnBwdArgs {
   float* relh_g;             // [B*heads, N, h]   (log2e-scaled)
   float* relw_g;             // [B*heads, N, W]
   __nv_bfloat16* dqkv;       // [B*N, 3C]
-  float* dTh;                // [2h-1, 64] fp32 atomics
-  float* dTw;                // [2W-1, 64]
+  float* dt_ws;              // [CTAs of kernel A][2h-1 + 2W-1][64] fp32 partial table gradients
   long long* trace;          // optional debug timeline of CTA (0,0,0): [kernel][role][iter][event]
   int debug;                 // bit 0: disable the software pipelining of kernel A (bring-up aid)
   int kv_stages;             // kernel A: K/V ring depth (3 hides the TMA latency; 2 when shared memory is short)
@@ -280,6 +279,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* my_relh = relh_gen + static_cast<size_t>(row) * ldr;
     float* my_gh = my_relh;  // rel_h[i] is consumed (tile i / R) before Gh'[i] is produced: same storage
     const size_t bh = static_cast<size_t>(b) * a.heads + head;
+    // this CTA's slice of the table-gradient workspace: [2h-1 + 2W-1][64] fp32 partial sums (plain stores; a
+    // reduction kernel adds the slices - 1664 CTAs x 10.6 K same-address atomics were ~half of this kernel's time)
+    float* ws_cta = a.dt_ws + (bh * gridDim.x + blockIdx.x) * static_cast<size_t>(2 * h - 1 + 2 * W - 1) * 64;
 
     // delta = rowsum(dO * O), LSE
     float delta = 0.f;
@@ -456,9 +458,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_x16(tS + lane_addr + mh * 64 + half * 32 + c0, v);
         tmem_wait_ld();
         if (tt < 2 * h - 1) {
+          float4* dst = reinterpret_cast<float4*>(ws_cta + static_cast<size_t>(tt) * 64 + half * 32 + c0);
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            atomicAdd(a.dTh + tt * 64 + half * 32 + c0 + c, __uint_as_float(v[c]) * 0.125f);
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(__uint_as_float(v[4 * q]) * 0.125f, __uint_as_float(v[4 * q + 1]) * 0.125f,
+                                 __uint_as_float(v[4 * q + 2]) * 0.125f, __uint_as_float(v[4 * q + 3]) * 0.125f);
         }
       }
     }
@@ -501,9 +505,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_x16(tS + lane_addr + half * 32 + c0, v);
       tmem_wait_ld();
       if (row < 2 * W - 1) {
+        float4* dst = reinterpret_cast<float4*>(ws_cta + static_cast<size_t>(2 * h - 1 + row) * 64 + half * 32 + c0);
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-          atomicAdd(a.dTw + row * 64 + half * 32 + c0 + c, __uint_as_float(v[c]) * 0.125f);
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_float4(__uint_as_float(v[4 * q]) * 0.125f, __uint_as_float(v[4 * q + 1]) * 0.125f,
+                               __uint_as_float(v[4 * q + 2]) * 0.125f, __uint_as_float(v[4 * q + 3]) * 0.125f);
       }
     }
     __nv_bfloat16* qrow = a.dqkv + (static_cast<size_t>(b) * a.N + t) * (3 * C) + head * 64 + half * 32;
@@ -823,11 +829,50 @@ extern "C" void pk_attn_bwd_set_trace(void* buf) { g_attnb_trace = static_cast<l
 
 // qkv / dqkv: bf16 [B*N, 3C];  O, dO: bf16 [B*N, C];  lse: fp32 [B*heads, N] from pk_attn_fwd
 // scratch buffers (caller-allocated): delta [B*heads*N], relh_g [B*heads*N*h], relw_g [B*heads*N*w] fp32
-// dTh [2h-1, 64], dTw [2w-1, 64]: fp32, accumulated atomically (caller zero-initialises)
+// dt_ws: pk_attn_bwd_ws_floats(B, heads, h, w) fp32 (per-CTA partial table gradients)
+// dTh [2h-1, 64], dTw [2w-1, 64]: fp32, ADDED to (caller zero-initialises or passes a running gradient)
+extern "C" long long pk_attn_bwd_ws_floats(int B, int heads, int h, int w) {
+  const long long ctas = static_cast<long long>((h * w + AB_BM - 1) / AB_BM) * heads * B;
+  return ctas * (2 * h - 1 + 2 * w - 1) * 64;
+}
+
+// dT[r][c] += sum over CTA slices ws[cta][r][c].  grid (rows, DT_STRIPES), block (64, 16): the slices are strided
+// over blockIdx.y / threadIdx.y, four loads in flight per thread, smem tree over threadIdx.y, one atomic per
+// (row, column, stripe).
+constexpr int DT_STRIPES = 4;
+__global__ void __launch_bounds__(1024)
+attn_dt_reduce_kernel(const float* __restrict__ ws, int nctas, int rows, int rows_h, float* __restrict__ dTh,
+                      float* __restrict__ dTw) {
+  __shared__ float red[16][64];
+  const int r = blockIdx.x, c = threadIdx.x;
+  const size_t slice = static_cast<size_t>(rows) * 64;
+  const float* p = ws + static_cast<size_t>(r) * 64 + c;
+  const int step = DT_STRIPES * 16;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = blockIdx.y * 16 + threadIdx.y;
+  for (; i + 3 * step < nctas; i += 4 * step) {
+    s0 += p[static_cast<size_t>(i) * slice];
+    s1 += p[static_cast<size_t>(i + step) * slice];
+    s2 += p[static_cast<size_t>(i + 2 * step) * slice];
+    s3 += p[static_cast<size_t>(i + 3 * step) * slice];
+  }
+  for (; i < nctas; i += step) s0 += p[static_cast<size_t>(i) * slice];
+  red[threadIdx.y][c] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 16; ++y) s += red[y][c];
+    float* dst = r < rows_h ? dTh + static_cast<size_t>(r) * 64 + c : dTw + static_cast<size_t>(r - rows_h) * 64 + c;
+    atomicAdd(dst, s);
+  }
+}
+
 extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
                            const void* tw, void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g,
-                           float* relw_g, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream) {
-  PK_CHECK(qkv && O && dO && lse && th && tw && dqkv && dTh && dTw && delta && relh_g && relw_g,
+                           float* relw_g, float* dt_ws, int B, int heads, int h, int w, int th_pad, int tw_pad,
+                           void* stream) {
+  PK_CHECK(qkv && O && dO && lse && th && tw && dqkv && dTh && dTw && delta && relh_g && relw_g && dt_ws,
            "pk_attn_bwd: null pointer");
   PK_CHECK(th_pad % 16 == 0 && tw_pad % 16 == 0 && th_pad >= 2 * h - 1 && tw_pad >= 2 * w - 1 &&
                th_pad <= 224 && tw_pad <= 112,
@@ -845,7 +890,7 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   a.dO = static_cast<const __nv_bfloat16*>(dO);
   a.lse = lse; a.delta = delta; a.relh_g = relh_g; a.relw_g = relw_g;
   a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  a.dTh = dTh; a.dTw = dTw;
+  a.dt_ws = dt_ws;
   a.trace = g_attnb_trace;
   a.debug = g_attnb_debug;
 
@@ -901,5 +946,11 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
       PK_CHECK(false, "pk_attn_bwd: token-grid width %d unsupported (must divide 112)", w);
   }
 #undef PK_ATTB_LAUNCH
+  {
+    const int rows = 2 * h - 1 + 2 * w - 1;
+    const int nctas = static_cast<int>(gridA.x * gridA.y * gridA.z);
+    attn_dt_reduce_kernel<<<dim3(rows, DT_STRIPES), dim3(64, 16), 0, st>>>(dt_ws, nctas, rows, 2 * h - 1, dTh, dTw);
+    PK_LAUNCH_CHECK("pk_attn_bwd(dT reduce)");
+  }
   return 0;
 }

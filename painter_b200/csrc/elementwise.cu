@@ -66,86 +66,110 @@ ln_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ ga
 }
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ dres);  dgamma += dy*xhat; dbeta += dy
-__global__ void __launch_bounds__(256, 2)
+// One block (C/4 threads, thread = one float4 column) walks groups of LNB_ROWS rows: the 2*LNB_ROWS row sums are
+// reduced warp-wise, exchanged through a double-buffered smem slab (one __syncthreads per group), and the
+// dgamma/dbeta partials stay in 8 registers per thread - no spills, >= 3 blocks per SM, LNB_ROWS*2 float4 loads
+// in flight per thread.  HBM-bound: 4 fp32 streams (dy, x, dres in; dx out).
+constexpr int LNB_ROWS = 4;
+__global__ void __launch_bounds__(256, 3)
 ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
               float* __restrict__ partials /* [gridDim.x][2C] */, int M, int C) {
-  extern __shared__ float red[];  // [8 warps][2][C]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nv = C / 128;
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4 gam[LN_MAX_V4], ag[LN_MAX_V4], ab[LN_MAX_V4];
-#pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i)
-    if (i < nv) {
-      gam[i] = __ldg(g4 + i * 32 + lane);
-      ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  __shared__ float4 xch[2][8][2 * LNB_ROWS / 4];  // [buffer][warp][s1[0..R) | s2[0..R)]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const float4 gam = reinterpret_cast<const float4*>(gamma)[tid];
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invC = 1.0f / C;
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
-    const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * lddy);
-    const float mu = mean[row], rs = rstd[row];
-    float4 xh[LN_MAX_V4], gd[LN_MAX_V4];
-    float s1 = 0.f, s2 = 0.f;
+  int it = 0;
+  for (int r0 = blockIdx.x * LNB_ROWS; r0 < M; r0 += gridDim.x * LNB_ROWS, ++it) {
+    float4 xh[LNB_ROWS], gd[LNB_ROWS], rv[LNB_ROWS];
+    float rs[LNB_ROWS], s[2 * LNB_ROWS];
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i)
-      if (i < nv) {
-        const float4 xv = xr[i * 32 + lane], dv = dr[i * 32 + lane];
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        gd[i] = make_float4(dv.x * gam[i].x, dv.y * gam[i].y, dv.z * gam[i].z, dv.w * gam[i].w);
-        s1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
-        s2 += (gd[i].x * xh[i].x + gd[i].y * xh[i].y) + (gd[i].z * xh[i].z + gd[i].w * xh[i].w);
-        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y;
-        ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
-        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
-      }
-    const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
-    float4* dxr = reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * C);
-    const float4* rr =
-        dres ? reinterpret_cast<const float4*>(dres + static_cast<size_t>(row) * C) : nullptr;
-#pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i)
-      if (i < nv) {
-        float4 o = make_float4(rs * (gd[i].x - c1 - xh[i].x * c2), rs * (gd[i].y - c1 - xh[i].y * c2),
-                               rs * (gd[i].z - c1 - xh[i].z * c2), rs * (gd[i].w - c1 - xh[i].w * c2));
-        if (rr) {
-          const float4 r = rr[i * 32 + lane];
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
-        dxr[i * 32 + lane] = o;
-      }
-  }
-  // block reduce of the dgamma/dbeta partials; one row of the partials buffer per block (no atomics: a second
-  // tiny kernel sums the rows)
-  float4* sg = reinterpret_cast<float4*>(red) + static_cast<size_t>(warp) * 2 * (C / 4);
-  float4* sb = sg + C / 4;
-#pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i)
-    if (i < nv) {
-      sg[i * 32 + lane] = ag[i];
-      sb[i * 32 + lane] = ab[i];
+    for (int u = 0; u < LNB_ROWS; ++u) {
+      const int row = min(r0 + u, M - 1);
+      xh[u] = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx)[tid];
+      gd[u] = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * lddy)[tid];
+      if (dres) rv[u] = reinterpret_cast<const float4*>(dres + static_cast<size_t>(row) * C)[tid];
     }
-  __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
-    float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[static_cast<size_t>(w) * 2 * C + c];
-    partials[static_cast<size_t>(blockIdx.x) * 2 * C + c] = s;
+    for (int u = 0; u < LNB_ROWS; ++u) {
+      const int row = min(r0 + u, M - 1);
+      const float mu = mean[row];
+      rs[u] = rstd[row];
+      const float4 dv = gd[u];
+      xh[u] = make_float4((xh[u].x - mu) * rs[u], (xh[u].y - mu) * rs[u], (xh[u].z - mu) * rs[u],
+                          (xh[u].w - mu) * rs[u]);
+      gd[u] = make_float4(dv.x * gam.x, dv.y * gam.y, dv.z * gam.z, dv.w * gam.w);
+      s[u] = (gd[u].x + gd[u].y) + (gd[u].z + gd[u].w);
+      s[LNB_ROWS + u] = (gd[u].x * xh[u].x + gd[u].y * xh[u].y) + (gd[u].z * xh[u].z + gd[u].w * xh[u].w);
+      if (r0 + u < M) {
+        ag.x += dv.x * xh[u].x; ag.y += dv.y * xh[u].y; ag.z += dv.z * xh[u].z; ag.w += dv.w * xh[u].w;
+        ab.x += dv.x; ab.y += dv.y; ab.z += dv.z; ab.w += dv.w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 2 * LNB_ROWS; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 2 * LNB_ROWS / 4; ++k)
+        xch[it & 1][warp][k] = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2 * LNB_ROWS; ++k) s[k] = 0.f;
+    for (int w = 0; w < nw; ++w) {
+#pragma unroll
+      for (int k = 0; k < 2 * LNB_ROWS / 4; ++k) {
+        const float4 t = xch[it & 1][w][k];
+        s[4 * k] += t.x; s[4 * k + 1] += t.y; s[4 * k + 2] += t.z; s[4 * k + 3] += t.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LNB_ROWS; ++u) {
+      if (r0 + u >= M) break;
+      const float c1 = s[u] * invC, c2 = s[LNB_ROWS + u] * invC;
+      float4 o = make_float4(rs[u] * (gd[u].x - c1 - xh[u].x * c2), rs[u] * (gd[u].y - c1 - xh[u].y * c2),
+                             rs[u] * (gd[u].z - c1 - xh[u].z * c2), rs[u] * (gd[u].w - c1 - xh[u].w * c2));
+      if (dres) {
+        o.x += rv[u].x; o.y += rv[u].y; o.z += rv[u].z; o.w += rv[u].w;
+      }
+      reinterpret_cast<float4*>(dx + static_cast<size_t>(r0 + u) * C)[tid] = o;
+    }
   }
+  // per-block partials, one row of the workspace per block (no atomics: a second small kernel sums the rows)
+  float4* pg = reinterpret_cast<float4*>(partials + static_cast<size_t>(blockIdx.x) * 2 * C);
+  pg[tid] = ag;
+  pg[C / 4 + tid] = ab;
 }
 
-// dgamma[c] += sum_b partials[b][c];  dbeta[c] += sum_b partials[b][C + c]
-__global__ void ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partials[static_cast<size_t>(b) * 2 * C + c];
-  if (c < C) dgamma[c] += s;
-  else dbeta[c - C] += s;
+// dgamma[c] += sum_b partials[b][c];  dbeta[c] += sum_b partials[b][C + c].   block (32, 8): 32 columns, the
+// rows strided over threadIdx.y, 4 loads in flight per thread.
+__global__ void __launch_bounds__(256)
+ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = threadIdx.y;
+  for (; b + 24 < nblocks; b += 32) {
+    s0 += partials[static_cast<size_t>(b) * 2 * C + c];
+    s1 += partials[static_cast<size_t>(b + 8) * 2 * C + c];
+    s2 += partials[static_cast<size_t>(b + 16) * 2 * C + c];
+    s3 += partials[static_cast<size_t>(b + 24) * 2 * C + c];
+  }
+  for (; b < nblocks; b += 8) s0 += partials[static_cast<size_t>(b) * 2 * C + c];
+  red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (c < C) dgamma[c] += s;
+    else dbeta[c - C] += s;
+  }
 }
 
 // =============================================================================================
@@ -487,8 +511,8 @@ extern "C" int pk_layernorm_fwd(const float* x, int ldx, const float* gamma, con
 }
 
 static int ln_bwd_grid(int M) {
-  int grid = sm_count() * 2;
-  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
+  int grid = sm_count() * 3;
+  if (grid > (M + LNB_ROWS - 1) / LNB_ROWS) grid = (M + LNB_ROWS - 1) / LNB_ROWS;
   return grid;
 }
 // fp32 workspace elements pk_layernorm_bwd needs (per-block partial sums of dgamma / dbeta)
@@ -500,19 +524,13 @@ extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int l
                                 const float* rstd, const float* gamma, const float* dres, float* dx,
                                 float* dgamma, float* dbeta, float* workspace, int M, int C, void* stream) {
   PK_CHECK(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "pk_layernorm_bwd: null pointer");
-  PK_CHECK(C % 128 == 0 && C <= 128 * LN_MAX_V4, "pk_layernorm_bwd: bad C=%d", C);
-  const size_t smem = static_cast<size_t>(8) * 2 * C * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4);
-    attr = true;
-  }
+  PK_CHECK(C % 128 == 0 && C <= 1024 && lddy % 4 == 0 && ldx % 4 == 0, "pk_layernorm_bwd: bad C=%d", C);
   const int grid = ln_bwd_grid(M);
-  ln_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, mean, rstd, gamma,
-                                                                      dres, dx, workspace, M, C);
+  ln_bwd_kernel<<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres,
+                                                                     dx, workspace, M, C);
   PK_LAUNCH_CHECK("pk_layernorm_bwd");
-  ln_bwd_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
-                                                                                         dbeta, C);
+  ln_bwd_reduce_kernel<<<2 * C / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
+                                                                                        dbeta, C);
   PK_LAUNCH_CHECK("pk_layernorm_bwd(reduce)");
   return 0;
 }

@@ -130,8 +130,11 @@ def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None):
     delta = torch.empty((B * heads * N,), dtype=torch.float32, device=dev)
     relh_g = torch.empty((B * heads * N * h,), dtype=torch.float32, device=dev)
     relw_g = torch.empty((B * heads * N * w,), dtype=torch.float32, device=dev)
+    L = lib()
+    L.pk_attn_bwd_ws_floats.restype = ctypes.c_longlong
+    dt_ws = torch.empty((int(L.pk_attn_bwd_ws_floats(B, heads, h, w)),), dtype=torch.float32, device=dev)
     check(lib().pk_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(th), _ptr(tw), _ptr(dqkv),
-                            _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), B, heads, h, w,
+                            _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), _ptr(dt_ws), B, heads, h, w,
                             th.shape[0], tw.shape[0], _stream()), "pk_attn_bwd")
     return dqkv, dTh, dTw
 

@@ -42,6 +42,8 @@ constexpr uint32_t A_SKV = A_SDS + 65536;       // kv_stages (2 or 3) x (K 14336
 constexpr uint32_t A_STH = A_SKV;               // epilogue: T_h reload (<= 28 KiB) over stage 0
 constexpr uint32_t A_STW = A_SKV + 28672;       // epilogue: T_w reload (<= 14 KiB) over stage 1
 // rel_h rows fp32 [128][h+1] follow the K/V stages (Gh' sums overwrite them in place): A_SKV + kv_stages * 28672
+// (separate K x4 / V x2 rings were tried: the MMA warp never waits on TMA here - the extra commit + barrier per tile
+// cost 4 % - so the coupled ring stays)
 
 struct AttnBwdArgs {
   int h, N, heads;
@@ -58,13 +60,18 @@ struct AttnBwdArgs {
   float* dt_ws;              // [CTAs of kernel A][2h-1 + 2W-1][64] fp32 partial table gradients
   long long* trace;          // optional debug timeline of CTA (0,0,0): [kernel][role][iter][event]
   int debug;                 // bit 0: disable the software pipelining of kernel A (bring-up aid)
-  int kv_stages;             // kernel A: K/V ring depth (3 hides the TMA latency; 2 when shared memory is short)
+  int kv_stages;             // kernel A: K/V ring depth (3 normally; 2 when shared memory is short)
 };
 
+// debug timeline: `ab_tr` (one predicate register per thread, set at kernel entry) selects the traced CTA, so a
+// stamp costs a clock read and a store instead of several special-register reads
+#define AB_TRACE_INIT()                                                                                    \
+  const bool ab_tr = a.trace != nullptr && blockIdx.x == 0 &&                                              \
+                     blockIdx.y == ((a.debug & 2) ? gridDim.y - 1 : 0) &&                                  \
+                     blockIdx.z == ((a.debug & 2) ? gridDim.z - 1 : 0)
 #define AB_TRACE(kern, role, it, ev)                                                                       \
   do {                                                                                                     \
-    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 16 &&         \
-        ((role) == 1 || (threadIdx.x & 31) == 0))                                                           \
+    if (ab_tr && (it) < 16 && ((role) == 1 || (threadIdx.x & 31) == 0))                                    \
       a.trace[(((kern) * 2 + (role)) * 16 + (it)) * 8 + (ev)] = clock64();                                   \
   } while (0)
 
@@ -74,6 +81,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmTh,
                    const __grid_constant__ CUtensorMap tmTw, const AttnBwdArgs a) {
   constexpr int R = AB_KT / W;
+  AB_TRACE_INIT();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_base = smem_u32(smem_raw);
   const uint32_t base = (raw_base + 1023u) & ~1023u;
@@ -85,13 +93,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t srelh_off = A_SKV + static_cast<uint32_t>(KS) * 28672u;
   float* relh_gen = reinterpret_cast<float*>(gen + srelh_off);
   const uint32_t bar0 = base + srelh_off + a.relh_bytes;
-  const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*3*/, bar_ke = bar0 + 32 /*3*/, bar_s = bar0 + 56 /*2*/,
-                 bar_p = bar0 + 72, bar_g = bar0 + 80, bar_gr = bar0 + 88, bar_e = bar0 + 96,
-                 bar_er = bar0 + 104, bar_t = bar0 + 112,
-                 bar_gw = bar0 + 128;  // G_w retired (single completion; bar_g completes twice and would alias)
-  const uint32_t holder = bar0 + 120;
+  const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*4*/, bar_ke = bar0 + 40 /*4*/,
+                 bar_s = bar0 + 104 /*2*/, bar_p = bar0 + 120, bar_g = bar0 + 128,
+                 bar_gr = bar0 + 136, bar_e = bar0 + 144, bar_er = bar0 + 152, bar_t = bar0 + 160,
+                 bar_gw = bar0 + 168;  // G_w retired (single completion; bar_g completes twice and would alias)
+  const uint32_t holder = bar0 + 176;
   volatile uint32_t* holder_gen =
-      reinterpret_cast<volatile uint32_t*>(gen + srelh_off + a.relh_bytes + 120);
+      reinterpret_cast<volatile uint32_t*>(gen + srelh_off + a.relh_bytes + 176);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AB_BM;
@@ -105,7 +113,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmdO);
     mbar_init(bar_q, 1);
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < 4; ++q) {
       mbar_init(bar_kf + 8 * q, 1);
       mbar_init(bar_ke + 8 * q, 1);
     }
@@ -143,6 +151,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_expect_tx(bar_kf + 8 * st, 2 * AB_KT * 128);
         tma_load_3d(sKV + st * 28672, &tmKV, bar_kf + 8 * st, C + head * 64, j * AB_KT, b);
         tma_load_3d(sKV + st * 28672 + 14336, &tmKV, bar_kf + 8 * st, 2 * C + head * 64, j * AB_KT, b);
+        AB_TRACE(0, 0, j, 5);
       }
       // epilogue: reload the tables as MN-major B operands once every main-loop MMA has retired
       mbar_wait(bar_e, 0);
@@ -193,10 +202,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint64_t dK0 = make_sdesc(sK, 16, 1024), dV0 = make_sdesc(sV, 16, 1024);
         const uint32_t tSb = tS + st * 224, tdPb = tSb + 112;
         mbar_wait(bar_kf + 8 * ks, (j / KS) & 1);
+        AB_TRACE(0, 0, j, 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss(tSb, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
+          AB_TRACE(0, 1, j, 6);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss(tdPb, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
           umma_commit(bar_s + 8 * st);
@@ -283,25 +294,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // reduction kernel adds the slices - 1664 CTAs x 10.6 K same-address atomics were ~half of this kernel's time)
     float* ws_cta = a.dt_ws + (bh * gridDim.x + blockIdx.x) * static_cast<size_t>(2 * h - 1 + 2 * W - 1) * 64;
 
-    // delta = rowsum(dO * O), LSE
-    float delta = 0.f;
-    {
-      const uint4* po = reinterpret_cast<const uint4*>(a.O + (static_cast<size_t>(b) * a.N + t) * C + head * 64);
-      const uint4* pd = reinterpret_cast<const uint4*>(a.dO + (static_cast<size_t>(b) * a.N + t) * C + head * 64);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint4 o = po[q], d = pd[q];
-        const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          delta += __uint_as_float(ow[e] << 16) * __uint_as_float(dw[e] << 16);
-          delta += __uint_as_float(ow[e] & 0xFFFF0000u) * __uint_as_float(dw[e] & 0xFFFF0000u);
-        }
-      }
-    }
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 0);
+    // delta = rowsum(dO * O) comes from attn_delta_kernel (coalesced pre-pass), LSE from the forward
+    const float delta = a.delta[bh * a.N + t];
     const float lse = a.lse[bh * a.N + t];
-    if (valid && half == 0) a.delta[bh * a.N + t] = delta;
 
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 1);
     // ---- rel_w -> registers (+ global for kernel B) ----
     float relw[W];
     {
@@ -325,35 +323,46 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(bar_gr);
       if (valid && half == 0) {
         float* dst = a.relw_g + (bh * a.N + t) * W;
+        if constexpr (W % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < W; ++j) dst[j] = relw[j];
+          for (int j = 0; j < W / 4; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(relw[4 * j], relw[4 * j + 1], relw[4 * j + 2], relw[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < W; ++j) dst[j] = relw[j];
+        }
       }
     }
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 2);
     // ---- rel_h -> smem (+ global): written by half 0, read by both halves after the first bar_s ----
     {
       mbar_wait(bar_g, 1);
       tc_fence_after();
-      if (half == 0) {
-        for (int c0 = 0; c0 < a.th_pad; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_x16(tS + lane_addr + c0, v);
-          tmem_wait_ld();
+      // 16-row chunks of the table alternate between the two column halves (both own the same 32 TMEM lanes)
+      for (int c0 = half * 16; c0 < a.th_pad; c0 += 32) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + c0, v);
+        tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int i = i_r + (h - 1) - (c0 + c);
-            if (i >= 0 && i < h) my_relh[i] = __uint_as_float(v[c]) * AB_LOG2E;
-          }
+        for (int c = 0; c < 16; ++c) {
+          const int i = i_r + (h - 1) - (c0 + c);
+          if (i >= 0 && i < h) my_relh[i] = __uint_as_float(v[c]) * AB_LOG2E;
         }
       }
-      if (valid && half == 0) {  // before the arrive: afterwards the other half may overwrite rel_h rows with Gh'
-        float* dst = a.relh_g + (bh * a.N + t) * h;
-        for (int i = 0; i < h; ++i) dst[i] = my_relh[i];
-      }
       tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(AB_SMX) : "memory");
+      // coalesced copy of the rel_h rows to global (kernel B reads them): warp per row.  It finishes before the
+      // arrive below, i.e. before any thread can start overwriting rel_h rows with Gh' (first bar_s needs all arrivals)
+      {
+        const int rows_valid = min(AB_BM, a.N - q0);
+        float* dst = a.relh_g + (bh * a.N + q0) * h;
+        for (int r = warp; r < rows_valid; r += AB_SMX / 32)
+          for (int i = lane; i < h; i += 32) dst[static_cast<size_t>(r) * h + i] = relh_gen[static_cast<size_t>(r) * ldr + i];
+      }
       __syncwarp();
       mbar_arrive(bar_gr);
     }
-
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 3);
     float gw[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) gw[j] = 0.f;
@@ -429,6 +438,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (row == 0 && half == 0) AB_TRACE(0, 1, j, 3);
     }
 
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 4);
     // ---------------- epilogue phase 1: Gh^ x 8 (bf16, K-major / MN-major dual view) ----------------
     // (dS is stored unscaled, so the accumulator holds 8 * dQ_bias + dS.K; the final read-out multiplies by 1/8)
     mbar_wait(bar_e, 0);
@@ -447,7 +457,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_er);
-    // ---------------- epilogue phase 2: dT_h atomics, then Gw^ x 8 ----------------
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 5);
+    // ---------------- epilogue phase 2: dT_h partials, then Gw^ x 8 ----------------
     mbar_wait(bar_e, 1);
     tc_fence_after();
     for (int mh = 0; mh * 128 < a.th_pad; ++mh) {
@@ -496,7 +507,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bar_er);
-    // ---------------- epilogue phase 3: dT_w atomics, dQ -> bf16 (each half owns 32 of the 64 columns) -----------
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 6);
+    // ---------------- epilogue phase 3: dT_w partials, dQ -> bf16 (each half owns 32 of the 64 columns) -----------
     mbar_wait(bar_e, 0);
     tc_fence_after();
 #pragma unroll
@@ -530,6 +542,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
+    if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 7);
   }
 
   tc_fence_before();
@@ -553,6 +566,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     const __grid_constant__ CUtensorMap tmdO, const AttnBwdArgs a) {
   constexpr int R = AB_KT / W;
+  AB_TRACE_INIT();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_base = smem_u32(smem_raw);
   const uint32_t base = (raw_base + 1023u) & ~1023u;
@@ -868,6 +882,34 @@ attn_dt_reduce_kernel(const float* __restrict__ ws, int nctas, int rows, int row
   }
 }
 
+// delta[b*heads + head][t] = sum_d O[b, t, head, d] * dO[b, t, head, d]: 8 lanes per (token, head) row of 64 bf16
+// (one 16-byte load each from O and dO, fully coalesced), xor-shuffle tree, lane 0 of the group stores.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                  float* __restrict__ delta, int B, int N, int heads) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t groups = static_cast<size_t>(B) * N * heads;
+  const size_t g = idx >> 3;
+  float acc = 0.f;
+  if (g < groups) {
+    const uint4 o = reinterpret_cast<const uint4*>(O)[idx], d = reinterpret_cast<const uint4*>(dO)[idx];
+    const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc += __uint_as_float(ow[e] << 16) * __uint_as_float(dw[e] << 16);
+      acc += __uint_as_float(ow[e] & 0xFFFF0000u) * __uint_as_float(dw[e] & 0xFFFF0000u);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (g < groups && (idx & 7) == 0) {
+    const size_t tok = g / heads, head = g - tok * heads;
+    const size_t b = tok / N, t = tok - b * N;
+    delta[(b * heads + head) * N + t] = acc;
+  }
+}
+
 extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
                            const void* tw, void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g,
                            float* relw_g, float* dt_ws, int B, int heads, int h, int w, int th_pad, int tw_pad,
@@ -918,6 +960,12 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   const size_t smemB = 1024 + B_BARS + 192;
   PK_CHECK(smemA <= 227 * 1024, "pk_attn_bwd: h=%d needs %zu B of shared memory", h, smemA);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const size_t threads = static_cast<size_t>(B) * N * heads * 8;
+    attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(O), static_cast<const __nv_bfloat16*>(dO), delta, B, N, heads);
+    PK_LAUNCH_CHECK("pk_attn_bwd(delta)");
+  }
   dim3 gridA((N + AB_BM - 1) / AB_BM, heads, B);
   const int R = AB_KT / w;
   dim3 gridB((h + R - 1) / R, heads, B);
@@ -929,9 +977,9 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
       cudaFuncSetAttribute(attn_bwd_dkv_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  \
       attr = true;                                                                                             \
     }                                                                                                          \
-    attn_bwd_dq_kernel<WW><<<gridA, AB_THREADS, smemA, st>>>(tmQ, tmKV, tmdO, tmTh, tmTw, a);                  \
+    if (!(a.debug & 4)) attn_bwd_dq_kernel<WW><<<gridA, AB_THREADS, smemA, st>>>(tmQ, tmKV, tmdO, tmTh, tmTw, a); \
     PK_LAUNCH_CHECK("pk_attn_bwd(dq)");                                                                        \
-    attn_bwd_dkv_kernel<WW><<<gridB, AB_THREADS, smemB, st>>>(tmQ, tmKV, tmdO, a);                             \
+    if (!(a.debug & 8)) attn_bwd_dkv_kernel<WW><<<gridB, AB_THREADS, smemB, st>>>(tmQ, tmKV, tmdO, a);          \
     PK_LAUNCH_CHECK("pk_attn_bwd(dkv)");                                                                       \
   } break;
   switch (w) {

@@ -33,10 +33,12 @@ do = (torch.randn(B * N, C, device="cuda") * 0.5).bfloat16()
 for _ in range(2):
     ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w)
 buf2 = torch.zeros(2 * 2 * 16 * 8, dtype=torch.int64, device="cuda")
+_lib.lib().pk_attn_bwd_debug(2 if os.environ.get("PK_TRACE_LAST") else 0)
 _lib.lib().pk_attn_bwd_set_trace(ctypes.c_void_p(buf2.data_ptr()))
 ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w)
 torch.cuda.synchronize()
 _lib.lib().pk_attn_bwd_set_trace(None)
+_lib.lib().pk_attn_bwd_debug(0)
 t2 = buf2.cpu().view(2, 2, 16, 8)
 for kern, kn in ((0, "dq "), (1, "dkv")):
     t0 = int(t2[kern, 0, 0, 0])
@@ -45,3 +47,10 @@ for kern, kn in ((0, "dq "), (1, "dkv")):
         sx = [int(t2[kern, 1, j, e]) - t0 for e in range(5)]
         print(f"{kn} it {j:2d}: mma top={m[0]:7d} s_next_issued={m[2]:7d} p_seen={m[3]:7d} dp_next_issued={m[5]:7d} "
               f"acc_issued={m[4]:7d} | smx wait={sx[0]:7d} bar_s_seen={sx[4]:7d} bar_dp_seen={sx[1]:7d} done={sx[2]:7d} arrived={sx[3]:7d}")
+
+ph = [int(t2[0, 1, 15, e]) - int(t2[0, 0, 0, 0]) for e in range(8)]
+print("dq phases (cycles rel. to mma top of it 0): start, delta_done, relw_done, relh_done, loop_done, ep1_done, ep2_done, end:", ph)
+
+print("dq: kf_seen(j) [stamp at tile j slot] and first-S-MMA-issued(j), relative:")
+t0 = int(t2[0, 0, 0, 0])
+print([ (int(t2[0, 0, j, 1]) - t0, int(t2[0, 1, j, 6]) - t0) for j in range(14)])

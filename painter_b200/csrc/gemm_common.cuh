@@ -336,7 +336,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
     for (int it = 0; it < 8; ++it) {
       zb[it] = pack4_bf16(xs[it]);
       const float4 zr = unpack4_bf16(zb[it]);
-      hb[it] = pack4_bf16(make_float4(gelu_erf(zr.x), gelu_erf(zr.y), gelu_erf(zr.z), gelu_erf(zr.w)));
+      hb[it] = pack4_bf16(make_float4(gelu_fast(zr.x), gelu_fast(zr.y), gelu_fast(zr.z), gelu_fast(zr.w)));
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -351,8 +351,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const float4 z = unpack4_bf16(auxh[it]);
-      o[it] = pack4_bf16(make_float4(xs[it].x * gelu_erf_grad(z.x), xs[it].y * gelu_erf_grad(z.y),
-                                     xs[it].z * gelu_erf_grad(z.z), xs[it].w * gelu_erf_grad(z.w)));
+      o[it] = pack4_bf16(make_float4(xs[it].x * gelu_fast_grad(z.x), xs[it].y * gelu_fast_grad(z.y),
+                                     xs[it].z * gelu_fast_grad(z.z), xs[it].w * gelu_fast_grad(z.w)));
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {

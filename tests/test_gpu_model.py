@@ -183,3 +183,15 @@ def test_no_cpu_fallback():
     x = torch.randn(1, 3, 128, 64)
     with pytest.raises(RuntimeError):
         m(x, x, torch.zeros(1, 8, 4), torch.ones(1, 3, 128, 64))
+
+
+def test_device_prefetcher_yields_every_pinned_batch_once():
+    """engine_train.py:52-56 moves each batch to the device at the top of the step; the prefetcher does the same
+    copy one step ahead on a side stream."""
+    from painter_b200.data_utils import DevicePrefetcher
+    host = [(torch.full((64, 64), float(i)).pin_memory(), torch.arange(16).add(i).pin_memory()) for i in range(5)]
+    seen = []
+    for a, b in DevicePrefetcher(iter(host), "cuda"):
+        assert a.is_cuda and b.is_cuda
+        seen.append((a.sum().item(), b[0].item()))
+    assert seen == [(64.0 * 64 * i, i) for i in range(5)]

@@ -22,7 +22,7 @@ namespace pk {
 
 constexpr int AB_BM = 128;
 constexpr int AB_KT = 112;
-constexpr int AB_THREADS = 320;   // TMA warp + MMA warp + 8 softmax warps
+constexpr int AB_THREADS = 352;   // 8 softmax warps + TMA warp + two tcgen05 issuing warps (scores | accumulations)
 constexpr int AB_SMX = 256;       // softmax threads
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
@@ -94,7 +94,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* relh_gen = reinterpret_cast<float*>(gen + srelh_off);
   const uint32_t bar0 = base + srelh_off + a.relh_bytes;
   const uint32_t bar_q = bar0, bar_kf = bar0 + 8 /*4*/, bar_ke = bar0 + 40 /*4*/,
-                 bar_s = bar0 + 104 /*2*/, bar_p = bar0 + 120, bar_g = bar0 + 128,
+                 bar_p1 = bar0 + 72, bar_df = bar0 + 80 /*2*/,
+                 bar_s = bar0 + 104 /*2*/, bar_p0 = bar0 + 120, bar_g = bar0 + 128,
                  bar_gr = bar0 + 136, bar_e = bar0 + 144, bar_er = bar0 + 152, bar_t = bar0 + 160,
                  bar_gw = bar0 + 168;  // G_w retired (single completion; bar_g completes twice and would alias)
   const uint32_t holder = bar0 + 176;
@@ -119,7 +120,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
-    mbar_init(bar_p, AB_SMX / 32);
+    mbar_init(bar_p0, AB_SMX / 32);
+    mbar_init(bar_p1, AB_SMX / 32);
+    mbar_init(bar_df, 1);
+    mbar_init(bar_df + 8, 1);
     mbar_init(bar_g, 1);
     mbar_init(bar_gr, AB_SMX);
     mbar_init(bar_e, 1);
@@ -192,35 +196,38 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_gr, 1);
       tc_fence_after();
       const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
-      const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
       const uint64_t dQ0 = make_sdesc(sQ, 16, 1024), ddO0 = make_sdesc(sdO, 16, 1024);
-      // software pipeline: S/dP of tile j+1 are issued before waiting for dS of tile j, so the tensor core works
-      // on the next scores while the softmax warps chew on the current ones
-      auto issue_scores = [&](int j) {
+      // Scores issuer: S/dP of tile j go out as soon as their TMEM buffer (j & 1) has been read by the softmax warps
+      // (tile j-2, barrier bar_p[j & 1]) and the K/V stage has landed; the accumulation MMAs are issued by warp 10,
+      // so neither stream waits behind the other's issue latency (a burst of 7-8 small MMAs costs 600-900 cycles).
+      for (int j = 0; j < num_tiles; ++j) {
         const int st = j & 1, ks = j % KS;
         const uint32_t sK = sKV + ks * 28672, sV = sK + 14336;
         const uint64_t dK0 = make_sdesc(sK, 16, 1024), dV0 = make_sdesc(sV, 16, 1024);
         const uint32_t tSb = tS + st * 224, tdPb = tSb + 112;
+        AB_TRACE(0, 0, j, 0);
+        if (j >= 2) mbar_wait(st ? bar_p1 : bar_p0, ((j >> 1) - 1) & 1);
         mbar_wait(bar_kf + 8 * ks, (j / KS) & 1);
         AB_TRACE(0, 0, j, 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss(tSb, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
-          AB_TRACE(0, 1, j, 6);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss(tdPb, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
           umma_commit(bar_s + 8 * st);
         }
         __syncwarp();
-      };
-      issue_scores(0);
+        AB_TRACE(0, 0, j, 2);
+      }
+    }
+  } else if (warp == 10) {
+    {
+      // ------------------------------ accumulation issuer (dQ, epilogue) ------------------------------
+      const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
       for (int j = 0; j < num_tiles; ++j) {
         const int st = j & 1;
-        AB_TRACE(0, 0, j, 0);
-        if (j + 1 < num_tiles && !(a.debug & 1)) issue_scores(j + 1);
-        AB_TRACE(0, 0, j, 2);
-        mbar_wait(bar_p, j & 1);
+        mbar_wait(st ? bar_p1 : bar_p0, (j >> 1) & 1);
         AB_TRACE(0, 0, j, 3);
         tc_fence_after();
         const uint64_t ddS0 = make_sdesc(sdS + st * 32768, 16, 1024);
@@ -230,11 +237,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int kk = 0; kk < AB_KT / 16; ++kk)
             umma_ss(tdQ, sdesc_add(ddS0, (kk >> 2) * 16384 + (kk & 3) * 32), sdesc_add(dK0, kk * 2048), idesc_dq,
                     (j | kk) != 0);
-          umma_commit(bar_ke + 8 * (j % KS));
+          umma_commit(bar_ke + 8 * (j % KS));   // K/V stage free (S/dP of this tile retired before p(j))
+          umma_commit(bar_df + 8 * st);         // dS buffer free
         }
         __syncwarp();
         AB_TRACE(0, 0, j, 4);
-        if (j + 1 < num_tiles && (a.debug & 1)) issue_scores(j + 1);
       }
       if (elect_one()) umma_commit(bar_e);  // completion #1 (parity 0): main loop retired
       __syncwarp();
@@ -363,26 +370,42 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(bar_gr);
     }
     if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 3);
+    // Per-score arithmetic on packed fp32 pairs (FFMA2 / FADD2 / FMUL2) when W is even (a pair of adjacent keys then
+    // shares its image row): bias add, scale-fma, (dP - delta), p * (.), row-sum and column-sum accumulations cost
+    // one issue slot per two scores.  Masking costs nothing: invalid image rows / query rows get a bias of -inf,
+    // so p = exp2(-inf) = 0 and dS = 0 (S and dP of out-of-range rows are finite: TMA zero-fills them).
+    constexpr bool PK2 = (W % 2 == 0);
     float gw[W];
+    f32x2 gw2[PK2 ? W / 2 : 1], relw2[PK2 ? W / 2 : 1];
 #pragma unroll
     for (int j = 0; j < W; ++j) gw[j] = 0.f;
+    if constexpr (PK2) {
+#pragma unroll
+      for (int j = 0; j < W / 2; ++j) {
+        gw2[j] = pack_f2(0.f, 0.f);
+        relw2[j] = pack_f2(relw[2 * j], relw[2 * j + 1]);
+      }
+    }
     const float sc = a.scale_log2;
+    const f32x2 sc2 = pack_f2(sc, sc), nd2 = pack_f2(-delta, -delta);
     for (int j = 0; j < num_tiles; ++j) {
       if (row == 0 && half == 0) AB_TRACE(0, 1, j, 0);
       mbar_wait(bar_s + 8 * (j & 1), (j >> 1) & 1);
       if (row == 0 && half == 0) AB_TRACE(0, 1, j, 1);
       tc_fence_after();
       float hb[RH], gh[RH];
+      f32x2 hb2[RH], gh2[RH];
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
         const int i = j * R + half * RH + r;
-        hb[r] = my_relh[i < h ? i : h - 1] - lse;
+        hb[r] = (i < h && valid) ? my_relh[i] - lse : -INFINITY;
         gh[r] = 0.f;
+        hb2[r] = pack_f2(hb[r], hb[r]);
+        gh2[r] = pack_f2(0.f, 0.f);
       }
-      const int keys_valid = (h - j * R) * W - cbase;  // columns of this half that are real keys
-      const bool full = keys_valid >= AB_KT / 2 && valid;
       const uint32_t tS_h = tS + (j & 1) * 224 + lane_addr + cbase, tdP_h = tS_h + 112;
       const uint32_t sdS_j = sdS + (j & 1) * 32768;
+      if (j >= 2) mbar_wait(bar_df + 8 * (j & 1), ((j >> 1) - 1) & 1);  // dQ(j-2) has drained this dS buffer
       // 56 columns per thread: 16 + 16 + 16 + 8
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
@@ -403,39 +426,63 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
         tmem_wait_ld();
-        float ds[16];
+        uint32_t dsb[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 16; c += 2) {
           if (c < nc) {
             const int kc = c0 + c;
-            float p = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]));
-            if (!full && (kc >= keys_valid || !valid)) p = 0.f;
-            ds[c] = p * (__uint_as_float(w[c]) - delta);
-            gh[kc / W] += ds[c];
-            gw[kc % W] += ds[c];
+            float d0, d1;
+            if constexpr (PK2) {
+              const f32x2 t2 = fma_f2(pack_u2(v[c], v[c + 1]), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2]));
+              float t0, t1;
+              unpack_f2(t2, t0, t1);
+              const f32x2 d2 = mul_f2(pack_f2(fast_exp2(t0), fast_exp2(t1)), add_f2(pack_u2(w[c], w[c + 1]), nd2));
+              gh2[kc / W] = add_f2(gh2[kc / W], d2);
+              gw2[(kc % W) / 2] = add_f2(gw2[(kc % W) / 2], d2);
+              unpack_f2(d2, d0, d1);
+            } else {
+              const int k1 = kc + 1;
+              d0 = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W])) *
+                   (__uint_as_float(w[c]) - delta);
+              d1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sc, hb[k1 / W] + relw[k1 % W])) *
+                   (__uint_as_float(w[c + 1]) - delta);
+              gh[kc / W] += d0;
+              gh[k1 / W] += d1;
+              gw[kc % W] += d0;
+              gw[k1 % W] += d1;
+            }
+            dsb[c / 2] = pack_bf16x2(d0, d1);
           }
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (q * 8 < nc) {
             const int g8 = ((cbase + c0) >> 3) + q;  // 8-column group inside the 112-wide tile
-            st_shared_v4(sdS_j + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4),
-                         pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]), pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]),
-                         pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]), pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+            st_shared_v4(sdS_j + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4), dsb[q * 4 + 0],
+                         dsb[q * 4 + 1], dsb[q * 4 + 2], dsb[q * 4 + 3]);
           }
         }
       }
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
         const int i = j * R + half * RH + r;
+        if constexpr (PK2) {
+          float g0, g1;
+          unpack_f2(gh2[r], g0, g1);
+          gh[r] = g0 + g1;
+        }
         if (i < h) my_gh[i] = gh[r];
       }
       if (row == 0 && half == 0) AB_TRACE(0, 1, j, 2);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
+      if (lane == 0) mbar_arrive((j & 1) ? bar_p1 : bar_p0);
       if (row == 0 && half == 0) AB_TRACE(0, 1, j, 3);
+    }
+    if constexpr (PK2) {
+#pragma unroll
+      for (int j = 0; j < W / 2; ++j) unpack_f2(gw2[j], gw[2 * j], gw[2 * j + 1]);
     }
 
     if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 4);
@@ -574,7 +621,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t sK = base + B_SK, sV = base + B_SV, sQ0 = base + B_SQ, sP = base + B_SP, sdS = base + B_SDS;
   const uint32_t bar0 = base + B_BARS;
   const uint32_t bar_kv = bar0, bar_qf = bar0 + 8 /*3*/, bar_qe = bar0 + 32 /*3*/, bar_s = bar0 + 56 /*2*/,
-                 bar_p = bar0 + 72, bar_o = bar0 + 80, bar_dp = bar0 + 88, bar_dsf = bar0 + 96;
+                 bar_p0 = bar0 + 72, bar_o = bar0 + 80, bar_dp = bar0 + 88, bar_dsf = bar0 + 96,
+                 bar_p1 = bar0 + 112, bar_pe = bar0 + 120 /*2*/;
   const uint32_t holder = bar0 + 104;
   volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B_BARS + 104);
 
@@ -598,7 +646,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_dp, 1);
     mbar_init(bar_dsf, 1);
-    mbar_init(bar_p, AB_SMX / 32);
+    mbar_init(bar_p0, AB_SMX / 32);
+    mbar_init(bar_p1, AB_SMX / 32);
+    mbar_init(bar_pe, 1);
+    mbar_init(bar_pe + 8, 1);
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
@@ -653,18 +704,31 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         __syncwarp();
       };
+      // Scores issuer.  S is double-buffered in TMEM: S(i+1) may go out once the softmax warps have consumed tile i-1
+      // (bar_p[(i-1) & 1]); dP has one buffer: dP(i+1) follows p(i).  The 16 accumulation MMAs of a tile are issued by
+      // warp 10, so they no longer sit between p(i) and dP(i+1) in one thread's issue stream.
       issue_s(0);
       issue_dp(0);
+      for (int i = 0; i + 1 < num_q; ++i) {
+        AB_TRACE(1, 0, i, 0);
+        if (i >= 1) mbar_wait(((i - 1) & 1) ? bar_p1 : bar_p0, ((i - 1) >> 1) & 1);
+        issue_s(i + 1);
+        AB_TRACE(1, 0, i, 2);
+        mbar_wait((i & 1) ? bar_p1 : bar_p0, (i >> 1) & 1);
+        tc_fence_after();
+        issue_dp(i + 1);
+        AB_TRACE(1, 0, i, 5);
+      }
+    }
+  } else if (warp == 10) {
+    {
+      // ------------------------------ accumulation issuer (dK, dV) ------------------------------
+      const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
       for (int i = 0; i < num_q; ++i) {
         const int qs = i % 3;
-        AB_TRACE(1, 0, i, 0);
-        if (i + 1 < num_q) issue_s(i + 1);
-        AB_TRACE(1, 0, i, 2);
-        mbar_wait(bar_p, i & 1);
+        mbar_wait((i & 1) ? bar_p1 : bar_p0, (i >> 1) & 1);
         AB_TRACE(1, 0, i, 3);
         tc_fence_after();
-        if (i + 1 < num_q) issue_dp(i + 1);
-        AB_TRACE(1, 0, i, 5);
         const uint64_t dQ0 = make_sdesc(sQ0 + qs * 32768, 16, 1024), ddO0 = make_sdesc(sQ0 + qs * 32768 + 16384, 16, 1024);
         const uint64_t dP0 = make_sdesc(sP + (i & 1) * 32768, 16384, 1024), ddS0 = make_sdesc(sdS, 16384, 1024);
         // dK[keys, d] += dS^T . Q first (releases the single dS buffer), then dV[keys, d] += P^T . dO
@@ -676,7 +740,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_ss(tdV, sdesc_add(dP0, kk * 2048), sdesc_add(ddO0, kk * 2048), idesc_tt, (i | kk) != 0);
-          umma_commit(bar_qe + 8 * qs);
+          umma_commit(bar_qe + 8 * qs);        // Q/dO stage free (S(i), dP(i) retired before p(i))
+          umma_commit(bar_pe + 8 * (i & 1));   // P buffer free
         }
         __syncwarp();
         AB_TRACE(1, 0, i, 4);
@@ -725,15 +790,25 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     };
     fetch(0);
     for (int i = 0; i < num_q; ++i) {
+      // packed fp32 pairs + -inf masking as in kernel A (invalid key rows of this tile / invalid query rows -> p = 0)
+      constexpr bool PK2 = (W % 2 == 0);
       const bool valid = valid_n;
       const float lse = lse_n, delta = delta_n;
       float hb[RH], relw[W];
+      f32x2 hb2[RH], relw2[PK2 ? W / 2 : 1];
 #pragma unroll
-      for (int r = 0; r < RH; ++r) hb[r] = hb_n[r] - lse;
+      for (int r = 0; r < RH; ++r) {
+        hb[r] = (valid && r * W < keys_valid) ? hb_n[r] - lse : -INFINITY;
+        hb2[r] = pack_f2(hb[r], hb[r]);
+      }
 #pragma unroll
       for (int j = 0; j < W; ++j) relw[j] = relw_n[j];
+      if constexpr (PK2) {
+#pragma unroll
+        for (int j = 0; j < W / 2; ++j) relw2[j] = pack_f2(relw[2 * j], relw[2 * j + 1]);
+      }
+      const f32x2 sc2 = pack_f2(sc, sc), nd2 = pack_f2(-delta, -delta);
       if (i + 1 < num_q) fetch(i + 1);
-      const bool full = keys_valid >= AB_KT / 2 && valid;
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 0);
       mbar_wait(bar_s + 8 * (i & 1), (i >> 1) & 1);
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 4);
@@ -762,18 +837,34 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         tmem_wait_ld();
-        float p[16], ds[16];
+        uint32_t pb[8], dsb[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 16; c += 2) {
           if (c < nc) {
             const int kc = c0 + c;
-            p[c] = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]));
-            if (!full && (kc >= keys_valid || !valid)) p[c] = 0.f;
-            ds[c] = p[c] * (__uint_as_float(w[c]) - delta);
+            float p0, p1, d0, d1;
+            if constexpr (PK2) {
+              const f32x2 t2 = fma_f2(pack_u2(v[c], v[c + 1]), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2]));
+              float t0, t1;
+              unpack_f2(t2, t0, t1);
+              p0 = fast_exp2(t0);
+              p1 = fast_exp2(t1);
+              const f32x2 d2 = mul_f2(pack_f2(p0, p1), add_f2(pack_u2(w[c], w[c + 1]), nd2));
+              unpack_f2(d2, d0, d1);
+            } else {
+              const int k1 = kc + 1;
+              p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]));
+              p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sc, hb[k1 / W] + relw[k1 % W]));
+              d0 = p0 * (__uint_as_float(w[c]) - delta);
+              d1 = p1 * (__uint_as_float(w[c + 1]) - delta);
+            }
+            pb[c / 2] = pack_bf16x2(p0, p1);
+            dsb[c / 2] = pack_bf16x2(d0, d1);
           }
         }
         if (!ds_free) {
           mbar_wait(bar_dsf, (i - 1) & 1);
+          if (i >= 2) mbar_wait(bar_pe + 8 * (i & 1), ((i >> 1) - 1) & 1);  // dV(i-2) has drained this P buffer
           ds_free = true;
         }
 #pragma unroll
@@ -781,11 +872,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (q * 8 < nc) {
             const int g8 = ((cbase + c0) >> 3) + q;
             const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
-            st_shared_v4(sP_i + off, pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]), pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]),
-                         pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5]), pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]));
-            st_shared_v4(sdS_i + off, pack_bf16x2(ds[q * 8 + 0], ds[q * 8 + 1]),
-                         pack_bf16x2(ds[q * 8 + 2], ds[q * 8 + 3]), pack_bf16x2(ds[q * 8 + 4], ds[q * 8 + 5]),
-                         pack_bf16x2(ds[q * 8 + 6], ds[q * 8 + 7]));
+            st_shared_v4(sP_i + off, pb[q * 4 + 0], pb[q * 4 + 1], pb[q * 4 + 2], pb[q * 4 + 3]);
+            st_shared_v4(sdS_i + off, dsb[q * 4 + 0], dsb[q * 4 + 1], dsb[q * 4 + 2], dsb[q * 4 + 3]);
           }
         }
       }
@@ -793,7 +881,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
+      if (lane == 0) mbar_arrive((i & 1) ? bar_p1 : bar_p0);
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 3);
     }
     // epilogue: accumulator row = key (jt*112 + row), rows >= 112 are padding; half 0 writes dK (x 1/8: dS is

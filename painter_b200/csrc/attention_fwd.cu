@@ -261,9 +261,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int i = j * R + r;
-        hb[r] = my_relh[i < h ? i : h - 1];
+        hb[r] = i < h ? my_relh[i] : -INFINITY;   // image rows past the end: bias -inf -> p = 0, no per-score select
       }
-      const int keys_valid = (h - j * R) * W;  // >= ATT_KT except in a partial last tile
       if (row == 0) ATT_TRACE(2, j, 0);
       mbar_wait(bar_s, j & 1);
       if (row == 0) ATT_TRACE(2, j, 1);
@@ -279,8 +278,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const int kc = c0 + c;
-            float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
-            if (kc >= keys_valid) tv = -INFINITY;
+            const float tv = fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]);
             mx = fmaxf(mx, tv);
           }
         }
@@ -289,11 +287,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // Optimistic single pass: p = exp2(t - m_ref) with the reference point of the previous tiles while the
       // tile max is tracked; only if some row's max outgrew m_ref by more than 2^8 is O rescaled and the pass
       // repeated (rare after the first tiles).  The result is exact for any threshold.
-      const bool full = keys_valid >= ATT_KT;
+      // The per-score arithmetic runs on packed fp32 pairs (FFMA2 / FADD2) when W is even: the softmax warps are
+      // issue-bound, a pair of adjacent keys shares its image row, so bias add, scale-fma and the row-sum
+      // accumulation cost one issue slot per two scores.
+      constexpr bool PK2 = (W % 2 == 0);
       for (int attempt = 0; attempt < 2; ++attempt) {
         float hbm[R];
+        f32x2 hbm2[R], relw2[PK2 ? W / 2 : 1];
 #pragma unroll
-        for (int r = 0; r < R; ++r) hbm[r] = hb[r] - m_ref;
+        for (int r = 0; r < R; ++r) {
+          hbm[r] = hb[r] - m_ref;
+          hbm2[r] = pack_f2(hbm[r], hbm[r]);
+        }
+        if constexpr (PK2) {
+#pragma unroll
+          for (int jj = 0; jj < W / 2; ++jj) relw2[jj] = pack_f2(relw[2 * jj], relw[2 * jj + 1]);
+        }
+        const f32x2 sc2 = pack_f2(sc, sc);
+        f32x2 l2 = pack_f2(0.f, 0.f);
         float mx = -INFINITY, l_tile = 0.f;
         uint32_t v[2][16];
         tmem_ld_x16(tS + lane_addr, v[0]);
@@ -304,13 +315,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (ci + 1 < ATT_KT / 16) tmem_ld_x16(tS + lane_addr + c0 + 16, v[(ci + 1) & 1]);
           float p[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
+          for (int c = 0; c < 16; c += 2) {
             const int kc = c0 + c;
-            float tv = fmaf(__uint_as_float(v[ci & 1][c]), sc, hbm[kc / W] + relw[kc % W]);
-            if (!full && kc >= keys_valid) tv = -INFINITY;
-            mx = fmaxf(mx, tv);
-            p[c] = fast_exp2(tv);
-            l_tile += p[c];
+            float t0, t1;
+            if constexpr (PK2) {
+              unpack_f2(fma_f2(pack_u2(v[ci & 1][c], v[ci & 1][c + 1]), sc2,
+                               add_f2(hbm2[kc / W], relw2[(kc % W) / 2])), t0, t1);
+            } else {
+              const int k1 = kc + 1;
+              t0 = fmaf(__uint_as_float(v[ci & 1][c]), sc, hbm[kc / W] + relw[kc % W]);
+              t1 = fmaf(__uint_as_float(v[ci & 1][c + 1]), sc, hbm[k1 / W] + relw[k1 % W]);
+            }
+            mx = fmaxf(mx, fmaxf(t0, t1));
+            p[c] = fast_exp2(t0);
+            p[c + 1] = fast_exp2(t1);
+            if constexpr (PK2) l2 = add_f2(l2, pack_f2(p[c], p[c + 1]));
+            else l_tile += p[c] + p[c + 1];
           }
           // 16 consecutive keys = two 16-byte chunks of this row inside K-block (c0 / 64)
           const uint32_t rowbase = sP + (c0 >> 6) * 16384 + row * 128;
@@ -323,6 +343,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                          "r"(pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5])), "r"(pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]))
                          : "memory");
           }
+        }
+        if constexpr (PK2) {
+          float l0, l1;
+          unpack_f2(l2, l0, l1);
+          l_tile = l0 + l1;
         }
         const bool grow = mx > 8.0f;  // relative to m_ref
         if (attempt == 1 || !__any_sync(0xffffffffu, grow)) {

@@ -127,7 +127,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       sch.init(g, tiles_mn, num_kb, cid, ncl);
       int mn, kb0, kb1;
       while (sch.next(mn, kb0, kb1)) {
-        const int m_blk = mn % g.num_m_tiles, n_blk = mn / g.num_m_tiles;
+        int m_blk, n_blk;
+        gemm_tile_coords(g, mn, m_blk, n_blk);
         const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
         const int n0 = n_blk * BN + static_cast<int>(rank) * BNh;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -203,7 +204,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     sch.init(g, tiles_mn, num_kb, cid, ncl);
     int mn, kb0, kb1;
     for (; sch.next(mn, kb0, kb1); ++it) {
-      const int m_blk = mn % g.num_m_tiles, n_blk = mn / g.num_m_tiles;
+      int m_blk, n_blk;
+        gemm_tile_coords(g, mn, m_blk, n_blk);
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();

@@ -54,6 +54,8 @@ struct GemmArgs {
   int splits, kb_per_split;  // split-K (epilogue accumulates with fp32 atomics when splits > 1)
   int streamk_units;         // > 0: stream-K (2-CTA kernel): every cluster owns this many consecutive
                              // (tile, k-block) units; partial tiles are added with fp32 atomics
+  int group_m;               // tile rasterisation: groups of group_m row blocks, the column blocks of a group
+                             // consecutive (0 = row blocks fastest, the 1-CTA kernel's order)
   PkEpilogue epi;
   ConvArgs conv;
   HeadArgs head;
@@ -100,6 +102,24 @@ struct GemmSched {
     return true;
   }
 };
+
+// Linear tile index -> (row block, column block).  Concurrent clusters should share operand blocks so that each is
+// fetched from HBM once and from L2 otherwise: with group_m = 1 the column blocks of one row block are adjacent
+// (A read once; right whenever B - weights, <= 40 MB - stays L2-resident: the N = 1024 GEMMs with K = 4096 read 2.3x
+// their algorithmic bytes with row blocks fastest); larger groups bound the B re-reads when B does not fit
+// (decoder_embed: 134 MB of weights).
+__device__ __forceinline__ void gemm_tile_coords(const GemmArgs& g, int mn, int& m_blk, int& n_blk) {
+  if (g.group_m <= 0) {
+    m_blk = mn % g.num_m_tiles;
+    n_blk = mn / g.num_m_tiles;
+    return;
+  }
+  const int per_group = g.group_m * g.num_n_tiles;
+  const int grp = mn / per_group, r = mn - grp * per_group;
+  const int gm = min(g.group_m, g.num_m_tiles - grp * g.group_m);
+  m_blk = grp * g.group_m + r % gm;
+  n_blk = r / gm;
+}
 
 // decoder-head parameters, refreshed per call by async D2D copies:
 // [0,64) conv bias | [64,128) LN2D gamma | [128,192) LN2D beta | [192,384) 1x1 weight [3][64] | [384,387) 1x1 bias

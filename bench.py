@@ -280,6 +280,12 @@ def main():
                       f"TF/s={f / t / 1e9:.0f}", file=sys.stderr)
         peak, peak_src = _peaks()
         achieved = flops / (gms / 1e3) / 1e12 if gms > 0 else 0.0
+        traffic = None      # DRAM bytes per launch of the GEMM kernel, from the committed ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")) as f:
+                traffic = json.load(f)["avg_dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": "images/sec ViT-L 896x448 MIM train step", "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": W_steps, "ms_per_step": ms_step,
@@ -296,7 +302,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "pk::gemm_bf16_kernel (tcgen05 GEMM, all linear layers fwd/bwd)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "peak_source": peak_src,
-                         "launches": len(gemm_log), "share_of_step": gms / ms_total, "traffic": None,
+                         "launches": len(gemm_log), "share_of_step": gms / ms_total, "traffic": traffic,
+                         "algorithmic_per_launch": flops / max(len(gemm_log), 1),
                          "step_mfu": value / world * FLOPS_PER_IMAGE_TRAIN / 1e12 / peak},
             "clocks": clk, "loss": last_loss,
         }

@@ -88,7 +88,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* gen = smem_raw + (base - raw_base);
 
   const uint32_t sQ = base + A_SQ, sdO = base + A_SDO, sdS = base + A_SDS, sKV = base + A_SKV;
-  const uint32_t sTh = base + A_STH, sTw = base + A_STW;
   const int KS = a.kv_stages;
   const uint32_t srelh_off = A_SKV + static_cast<uint32_t>(KS) * 28672u;
   float* relh_gen = reinterpret_cast<float*>(gen + srelh_off);
@@ -108,6 +107,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int C = a.heads * 64;
   const int h = a.h;
   const int num_tiles = (h + R - 1) / R;
+  // Epilogue copies of the tables (MN-major B operands).  With a 3-deep ring the stage last used by tile
+  // num_tiles-3 idles for the final two tiles: if both tables fit there they are reloaded two tiles early and their
+  // TMA latency disappears from the epilogue; otherwise they land on stages 0/1 after the main loop has retired.
+  const bool early_tables =
+      KS == 3 && num_tiles >= 3 && static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u <= 28672u;
+  const uint32_t sTh = early_tables ? sKV + static_cast<uint32_t>(num_tiles % 3) * 28672u : base + A_STH;
+  const uint32_t sTw = early_tables ? sTh + static_cast<uint32_t>(a.th_pad) * 128u : base + A_STW;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -157,8 +163,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_3d(sKV + st * 28672 + 14336, &tmKV, bar_kf + 8 * st, 2 * C + head * 64, j * AB_KT, b);
         AB_TRACE(0, 0, j, 5);
       }
-      // epilogue: reload the tables as MN-major B operands once every main-loop MMA has retired
-      mbar_wait(bar_e, 0);
+      // epilogue: reload the tables as MN-major B operands (early into the idle stage, else once every main-loop
+      // MMA has retired)
+      if (early_tables) mbar_wait(bar_ke + 8 * (num_tiles % 3), ((num_tiles - 3) / 3) & 1);
+      else mbar_wait(bar_e, 0);
       mbar_expect_tx(bar_t, static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u);
       tma_load_2d(sTh, &tmTh, bar_t, 0, 0);
       tma_load_2d(sTw, &tmTw, bar_t, 0, 0);
@@ -621,8 +629,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t sK = base + B_SK, sV = base + B_SV, sQ0 = base + B_SQ, sP = base + B_SP, sdS = base + B_SDS;
   const uint32_t bar0 = base + B_BARS;
   const uint32_t bar_kv = bar0, bar_qf = bar0 + 8 /*3*/, bar_qe = bar0 + 32 /*3*/, bar_s = bar0 + 56 /*2*/,
-                 bar_p0 = bar0 + 72, bar_o = bar0 + 80, bar_dp = bar0 + 88, bar_dsf = bar0 + 96,
-                 bar_p1 = bar0 + 112, bar_pe = bar0 + 120 /*2*/;
+                 bar_p0 = bar0 + 72, bar_o = bar0 + 80, bar_dp = bar0 + 88 /* +136 */, bar_dsf = bar0 + 96,
+                 bar_p1 = bar0 + 112, bar_pe = bar0 + 120 /*2*/, bar_dp1 = bar0 + 136, bar_sc = bar0 + 144 /*2*/;
   const uint32_t holder = bar0 + 104;
   volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B_BARS + 104);
 
@@ -645,6 +653,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_dp, 1);
+    mbar_init(bar_dp1, 1);
+    mbar_init(bar_sc, AB_SMX / 32);
+    mbar_init(bar_sc + 8, AB_SMX / 32);
     mbar_init(bar_dsf, 1);
     mbar_init(bar_p0, AB_SMX / 32);
     mbar_init(bar_p1, AB_SMX / 32);
@@ -658,8 +669,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
-  // S double-buffered (columns 0 / 112), dP single (224), dV (336), dK (400)
-  const uint32_t tS = tmem, tdP = tmem + 224, tdV = tmem + 336, tdK = tmem + 400;
+  // Three 112-column score buffers rotate between S and dP (dV at 336, dK at 400): tile i keeps S in buffer
+  // s_i = (3 - i % 3) % 3 and dP in d_i = (s_i + 1) % 3.  S(i+1) lands in the third buffer while tile i is being
+  // processed; dP(i+1) reuses S(i)'s buffer as soon as the softmax warps have finished their first pass (p = exp2(.)
+  // needs S only), so neither score MMA of the next tile waits for the end of the current one.
+  const uint32_t tS = tmem, tdV = tmem + 336, tdK = tmem + 400;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -690,7 +704,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ss(tS + (i & 1) * 112, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
+            umma_ss(tS + ((3 - i % 3) % 3) * 112, sdesc_add(dQ0, k * 32), sdesc_add(dK0, k * 32), idesc_s, k != 0);
           umma_commit(bar_s + 8 * (i & 1));
         }
         __syncwarp();
@@ -699,25 +713,29 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint64_t ddO0 = make_sdesc(sQ0 + (i % 3) * 32768 + 16384, 16, 1024);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tdP, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
-          umma_commit(bar_dp);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS + ((4 - i % 3) % 3) * 112, sdesc_add(ddO0, k * 32), sdesc_add(dV0, k * 32), idesc_s, k != 0);
+          umma_commit((i & 1) ? bar_dp1 : bar_dp);
         }
         __syncwarp();
       };
-      // Scores issuer.  S is double-buffered in TMEM: S(i+1) may go out once the softmax warps have consumed tile i-1
-      // (bar_p[(i-1) & 1]); dP has one buffer: dP(i+1) follows p(i).  The 16 accumulation MMAs of a tile are issued by
-      // warp 10, so they no longer sit between p(i) and dP(i+1) in one thread's issue stream.
+      // Scores issuer (buffer rotation above): dP(i+1) after the first softmax pass of tile i (bar_sc), S(i+2) after
+      // the whole of tile i (bar_p).  The 16 accumulation MMAs of a tile are issued by warp 10.
       issue_s(0);
       issue_dp(0);
+      if (num_q > 1) issue_s(1);
       for (int i = 0; i + 1 < num_q; ++i) {
         AB_TRACE(1, 0, i, 0);
-        if (i >= 1) mbar_wait(((i - 1) & 1) ? bar_p1 : bar_p0, ((i - 1) >> 1) & 1);
-        issue_s(i + 1);
-        AB_TRACE(1, 0, i, 2);
-        mbar_wait((i & 1) ? bar_p1 : bar_p0, (i >> 1) & 1);
+        mbar_wait(bar_sc + 8 * (i & 1), (i >> 1) & 1);
         tc_fence_after();
         issue_dp(i + 1);
         AB_TRACE(1, 0, i, 5);
+        if (i + 2 < num_q) {
+          mbar_wait((i & 1) ? bar_p1 : bar_p0, (i >> 1) & 1);
+          tc_fence_after();
+          issue_s(i + 2);
+          AB_TRACE(1, 0, i, 2);
+        }
       }
     }
   } else if (warp == 10) {
@@ -812,60 +830,46 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 0);
       mbar_wait(bar_s + 8 * (i & 1), (i >> 1) & 1);
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 4);
-      mbar_wait(bar_dp, i & 1);
-      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 1);
       tc_fence_after();
-      const uint32_t tS_h = tS + (i & 1) * 112 + lane_addr + cbase, tdP_h = tdP + lane_addr + cbase;
+      const int sbuf = (3 - i % 3) % 3, dbuf = (sbuf + 1) % 3;
+      const uint32_t tS_h = tS + sbuf * 112 + lane_addr + cbase, tdP_h = tS + dbuf * 112 + lane_addr + cbase;
       const uint32_t sP_i = sP + (i & 1) * 32768, sdS_i = sdS;
-      bool ds_free = i == 0;  // the dK MMAs of tile i-1 must have drained the dS buffer before it is rewritten
+      if (i >= 2) mbar_wait(bar_pe + 8 * (i & 1), ((i >> 1) - 1) & 1);  // dV(i-2) has drained this P buffer
+      // ---- pass 1: p = exp2(scale * S + bias - lse) (fp32, kept in registers for pass 2), P -> smem as bf16 ----
+      f32x2 pp[AB_KT / 4];   // 56 probabilities as 28 packed pairs
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c0 = ci * 16;
         const int nc = ci < 3 ? 16 : 8;
-        uint32_t v[16], w[16];
+        uint32_t v[16];
         if (ci < 3) {
           tmem_ld_x16(tS_h + c0, v);
-          tmem_ld_x16(tdP_h + c0, w);
         } else {
-          uint32_t v8[8], w8[8];
+          uint32_t v8[8];
           tmem_ld_x8(tS_h + c0, v8);
-          tmem_ld_x8(tdP_h + c0, w8);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            v[c] = v8[c];
-            w[c] = w8[c];
-          }
+          for (int c = 0; c < 8; ++c) v[c] = v8[c];
         }
         tmem_wait_ld();
-        uint32_t pb[8], dsb[8];
+        uint32_t pb[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
           if (c < nc) {
             const int kc = c0 + c;
-            float p0, p1, d0, d1;
+            float p0, p1;
             if constexpr (PK2) {
-              const f32x2 t2 = fma_f2(pack_u2(v[c], v[c + 1]), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2]));
               float t0, t1;
-              unpack_f2(t2, t0, t1);
+              unpack_f2(fma_f2(pack_u2(v[c], v[c + 1]), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2])), t0, t1);
               p0 = fast_exp2(t0);
               p1 = fast_exp2(t1);
-              const f32x2 d2 = mul_f2(pack_f2(p0, p1), add_f2(pack_u2(w[c], w[c + 1]), nd2));
-              unpack_f2(d2, d0, d1);
             } else {
               const int k1 = kc + 1;
               p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]));
               p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sc, hb[k1 / W] + relw[k1 % W]));
-              d0 = p0 * (__uint_as_float(w[c]) - delta);
-              d1 = p1 * (__uint_as_float(w[c + 1]) - delta);
             }
+            pp[kc / 2] = pack_f2(p0, p1);
             pb[c / 2] = pack_bf16x2(p0, p1);
-            dsb[c / 2] = pack_bf16x2(d0, d1);
           }
-        }
-        if (!ds_free) {
-          mbar_wait(bar_dsf, (i - 1) & 1);
-          if (i >= 2) mbar_wait(bar_pe + 8 * (i & 1), ((i >> 1) - 1) & 1);  // dV(i-2) has drained this P buffer
-          ds_free = true;
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -873,6 +877,54 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int g8 = ((cbase + c0) >> 3) + q;
             const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
             st_shared_v4(sP_i + off, pb[q * 4 + 0], pb[q * 4 + 1], pb[q * 4 + 2], pb[q * 4 + 3]);
+          }
+        }
+      }
+      // S(i) is consumed: its TMEM buffer may take dP(i+1)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sc + 8 * (i & 1));
+      // ---- pass 2: dS = p * (dP - delta) -> smem as bf16 ----
+      mbar_wait((i & 1) ? bar_dp1 : bar_dp, (i >> 1) & 1);
+      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 1);
+      tc_fence_after();
+      if (i >= 1) mbar_wait(bar_dsf, (i - 1) & 1);   // the dK MMAs of tile i-1 have drained the dS buffer
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ci * 16;
+        const int nc = ci < 3 ? 16 : 8;
+        uint32_t w[16];
+        if (ci < 3) {
+          tmem_ld_x16(tdP_h + c0, w);
+        } else {
+          uint32_t w8[8];
+          tmem_ld_x8(tdP_h + c0, w8);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) w[c] = w8[c];
+        }
+        tmem_wait_ld();
+        uint32_t dsb[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          if (c < nc) {
+            const int kc = c0 + c;
+            float d0, d1;
+            if constexpr (PK2) {
+              unpack_f2(mul_f2(pp[kc / 2], add_f2(pack_u2(w[c], w[c + 1]), nd2)), d0, d1);
+            } else {
+              float p0, p1;
+              unpack_f2(pp[kc / 2], p0, p1);
+              d0 = p0 * (__uint_as_float(w[c]) - delta);
+              d1 = p1 * (__uint_as_float(w[c + 1]) - delta);
+            }
+            dsb[c / 2] = pack_bf16x2(d0, d1);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q * 8 < nc) {
+            const int g8 = ((cbase + c0) >> 3) + q;
+            const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
             st_shared_v4(sdS_i + off, dsb[q * 4 + 0], dsb[q * 4 + 1], dsb[q * 4 + 2], dsb[q * 4 + 3]);
           }
         }

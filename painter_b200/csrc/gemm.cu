@@ -393,7 +393,8 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
       }
     }
     // rasterisation: keep B L2-resident when it fits, otherwise sweep the columns inside groups of 8 row blocks
-    g2.group_m = (static_cast<long long>(N) * K * 2 <= (40ll << 20)) ? 1 : 8;
+    // (stream-K calls with a large B keep the row-fastest order: measured 1006 vs 918 TF/s on the decoder wgrad)
+    g2.group_m = (static_cast<long long>(N) * K * 2 <= (40ll << 20)) ? 1 : (g2.streamk_units > 0 ? 0 : 8);
     return launch_gemm2(A, B, lda, ldb, g2, static_cast<cudaStream_t>(stream));
   }
 

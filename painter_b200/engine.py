@@ -33,10 +33,16 @@ def bf16_weight(p, shape2d=None):
     return w
 
 
-def _wgrad(dy_bf16, x_bf16):
-    """dW[out, in] = dY^T . X  (both operands read MN-major; split-K when the tile count is small)."""
-    out = torch.zeros((dy_bf16.shape[1], x_bf16.shape[1]), dtype=torch.float32, device=dy_bf16.device)
+def _wgrad(dy_bf16, x_bf16, out=None):
+    """dW[out, in] = dY^T . X  (both operands read MN-major; stream-K over the zero-initialised fp32 output)."""
+    if out is None:
+        out = torch.zeros((dy_bf16.shape[1], x_bf16.shape[1]), dtype=torch.float32, device=dy_bf16.device)
     return ops.gemm(dy_bf16, x_bf16, trans_a=True, trans_b=True, kind=EPI_F32, out=out, accumulate=2)
+
+
+def th_rows(size):
+    """Rows of a decomposed rel-pos table for a grid side `size` (vitdet_utils.get_rel_pos: 2 * size - 1)."""
+    return 2 * size - 1
 
 
 def resize_rel_table(table, size):
@@ -142,17 +148,25 @@ class BlockFn(torch.autograd.Function):
         dev = x.device
         dx2 = dx2.contiguous()
         H4 = wfc1.shape[0]
-        # one zero-filled slab for every small reduction target of this block (LN affine grads, bias grads)
-        small = torch.zeros(4 * C + 2 * C + H4 + 3 * C, dtype=torch.float32, device=dev)
+        # ONE zero-filled slab per block backward: every accumulation target of the block (LN affine grads, bias
+        # grads, the four weight gradients the stream-K GEMMs add into, the rel-pos table gradients) is a view of it
+        Lh, Lw = th_rows(h if ws == 0 else ws), th_rows(w if ws == 0 else ws)
+        n_small = 4 * C + 2 * C + H4 + 3 * C
+        sizes = [n_small, 3 * C * C, C * C, H4 * C, C * H4, Lh * 64, Lw * 64]
+        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        small, g_qkv, g_proj, g_fc1, g_fc2, g_th, g_tw = torch.split(slab, sizes)
+        g_qkv, g_proj = g_qkv.view(3 * C, C), g_proj.view(C, C)
+        g_fc1, g_fc2 = g_fc1.view(H4, C), g_fc2.view(C, H4)
+        g_th, g_tw = g_th.view(Lh, 64), g_tw.view(Lw, 64)
         dn1w, dn1b, dn2w, dn2b = small[0:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
         dfc2_b, dproj_b = small[4 * C:5 * C], small[5 * C:6 * C]
         dfc1_b, dqkv_b = small[6 * C:6 * C + H4], small[6 * C + H4:]
         # ---- MLP branch ----
         dy, _ = ops.scale_cast_colsum(dx2, drop_m, N, colsum_out=dfc2_b)
-        dfc2_w = _wgrad(dy, hact)
+        dfc2_w = _wgrad(dy, hact, out=g_fc2)
         dz = ops.gemm(dy, wfc2, trans_b=True, kind=EPI_DGELU, aux=z)
         ops.colsum_bf16(dz, out=dfc1_b)
-        dfc1_w = _wgrad(dz, v)
+        dfc1_w = _wgrad(dz, v, out=g_fc1)
         dv = ops.gemm(dz, wfc1, trans_b=True, kind=EPI_F32)
         dx1 = ops.layernorm_bwd(dv, x1, mean2, rstd2, n2w, dn2w, dn2b, dres=dx2)
         # ---- attention branch ----
@@ -160,14 +174,14 @@ class BlockFn(torch.autograd.Function):
         if ws > 0:
             da = ops.window_partition_bf16(da, Bp, h, w, ws)
             Bw = da.shape[0] // (ws * ws)
-        dproj_w = _wgrad(da, ao)
+        dproj_w = _wgrad(da, ao, out=g_proj)
         dao = ops.gemm(da, wproj, trans_b=True, kind=EPI_BF16)
         if ws > 0:
-            dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bw, heads, ws, ws)
+            dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bw, heads, ws, ws, dT_out=(g_th, g_tw))
         else:
-            dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bp, heads, h, w)
+            dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bp, heads, h, w, dT_out=(g_th, g_tw))
         ops.colsum_bf16(dqkv, out=dqkv_b)
-        dqkv_w = _wgrad(dqkv, u)
+        dqkv_w = _wgrad(dqkv, u, out=g_qkv)
         du = ops.gemm(dqkv, wqkv, trans_b=True, kind=EPI_F32)
         if ws > 0:
             du = ops.window_unpartition(du, Bp, h, w, ws)   # gradients at padded tokens are dropped

@@ -118,15 +118,20 @@ def attn_fwd(qkv, th, tw, B, heads, h, w, need_lse=True):
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None):
+def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None, dT_out=None):
     """Fused attention backward.  Returns (dqkv bf16 [B*N, 3C], dTh fp32 [2h-1, 64], dTw fp32 [2w-1, 64])."""
     N, C = h * w, heads * 64
     _req(dout, torch.bfloat16, "dout")
     assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
     dev = qkv.device
     dqkv = torch.empty_like(qkv)
-    dTh = torch.zeros((2 * h - 1, 64), dtype=torch.float32, device=dev)
-    dTw = torch.zeros((2 * w - 1, 64), dtype=torch.float32, device=dev)
+    if dT_out is not None:       # caller-provided, zero-initialised (or running) fp32 accumulators
+        dTh, dTw = dT_out
+        assert tuple(dTh.shape) == (2 * h - 1, 64) and tuple(dTw.shape) == (2 * w - 1, 64)
+        assert dTh.is_contiguous() and dTw.is_contiguous() and dTh.dtype == torch.float32
+    else:
+        dTh = torch.zeros((2 * h - 1, 64), dtype=torch.float32, device=dev)
+        dTw = torch.zeros((2 * w - 1, 64), dtype=torch.float32, device=dev)
     delta = torch.empty((B * heads * N,), dtype=torch.float32, device=dev)
     relh_g = torch.empty((B * heads * N * h,), dtype=torch.float32, device=dev)
     relw_g = torch.empty((B * heads * N * w,), dtype=torch.float32, device=dev)

@@ -100,8 +100,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_step_time(threads, reps=1):
-    """Oracle port (torch-CPU fp32 restatement of the reference), B=1 896x448 train step (fwd + bwd)."""
+def cpu_port_step_time(threads, reps=1, budget_s=None, min_reps=1):
+    """Oracle port (torch-CPU fp32 restatement of the reference), B=1 896x448 train step (fwd + bwd).
+    With `budget_s` the loop stops early once that much wall time is spent (after at least `min_reps` steps), so the
+    CPU legs stay bounded whatever --steps is."""
     import torch
     from oracle import painter_oracle as po
     from oracle.synth import synth_state_dict
@@ -118,6 +120,8 @@ def cpu_port_step_time(threads, reps=1):
         loss, _, _ = po.forward(sd, cfg, imgs, tgts, mask, valid, drops=drops)
         loss.backward()
         times.append(time.perf_counter() - t0)
+        if budget_s is not None and len(times) >= min_reps and sum(times) > budget_s:
+            break
     return times
 
 
@@ -126,7 +130,8 @@ def run_reference(args):
     if rank != 0:
         return
     threads = min(os.cpu_count() or 1, 32)   # beyond ~32 threads torch-CPU eager slows down (oversubscription)
-    t = cpu_port_step_time(threads, reps=args.warmup + args.steps)[args.warmup:]
+    # bounded sample: one warm-up step, then up to --steps timed steps or ~150 s of CPU work, whichever comes first
+    t = cpu_port_step_time(threads, reps=1 + args.steps, budget_s=150.0, min_reps=2)[1:]
     ms = 1e3 * sum(t) / len(t)
     val = 1.0 / (ms / 1e3)
     line = {
@@ -136,7 +141,7 @@ def run_reference(args):
         "config": {"workload": "ViT-L 896x448 MIM train step (fwd+bwd), B=1 per step on host cores",
                    "global_batch": 1, "parallelism": "cpu"},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} x (B=1 forward+backward) of the oracle port, torch-CPU fp32"},
+                         "sample": f"{len(t)} x (B=1 forward+backward) of the oracle port, torch-CPU fp32, after 1 warm-up"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -144,11 +149,14 @@ def run_reference(args):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (N > 1)")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="diagnostic only; the reported step includes AdamW")
@@ -181,7 +189,8 @@ def main():
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=args.bucket_mb)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, fused=True)
 
     host = [t.pin_memory() for t in _batch(B, dist_utils.rank_seed(0, rank) % 9973)]

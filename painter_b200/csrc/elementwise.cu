@@ -70,16 +70,22 @@ ln_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ ga
 // reduced warp-wise, exchanged through a double-buffered smem slab (one __syncthreads per group), and the
 // dgamma/dbeta partials stay in 8 registers per thread - no spills, >= 3 blocks per SM, LNB_ROWS*2 float4 loads
 // in flight per thread.  HBM-bound: 4 fp32 streams (dy, x, dres in; dx out).
+// FUSE: the caller also needs bf16(rowscale[row / rows_per_group] * dx) (the next GEMM's operand after DropPath) and
+// its column sums (that GEMM's bias gradient): emitted here instead of re-reading dx in a second kernel; the
+// column sums ride in a third partials block.
 constexpr int LNB_ROWS = 4;
-__global__ void __launch_bounds__(256, 3)
+template <bool FUSE>
+__global__ void __launch_bounds__(256, FUSE ? 2 : 3)
 ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
-              float* __restrict__ partials /* [gridDim.x][2C] */, int M, int C) {
+              float* __restrict__ partials /* [gridDim.x][2C or 3C] */, int M, int C,
+              const float* __restrict__ rowscale, int rows_per_group, __nv_bfloat16* __restrict__ dx_bf16) {
   __shared__ float4 xch[2][8][2 * LNB_ROWS / 4];  // [buffer][warp][s1[0..R) | s2[0..R)]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const float4 gam = reinterpret_cast<const float4*>(gamma)[tid];
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acs = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invC = 1.0f / C;
   int it = 0;
   for (int r0 = blockIdx.x * LNB_ROWS; r0 < M; r0 += gridDim.x * LNB_ROWS, ++it) {
@@ -137,30 +143,42 @@ ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ 
         o.x += rv[u].x; o.y += rv[u].y; o.z += rv[u].z; o.w += rv[u].w;
       }
       reinterpret_cast<float4*>(dx + static_cast<size_t>(r0 + u) * C)[tid] = o;
+      if constexpr (FUSE) {
+        const float sc = rowscale ? rowscale[(r0 + u) / rows_per_group] : 1.f;
+        o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
+        acs.x += o.x; acs.y += o.y; acs.z += o.z; acs.w += o.w;
+        uint2 pk2;
+        pk2.x = pack_bf16x2(o.x, o.y);
+        pk2.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(r0 + u) * C)[tid] = pk2;
+      }
     }
   }
   // per-block partials, one row of the workspace per block (no atomics: a second small kernel sums the rows)
-  float4* pg = reinterpret_cast<float4*>(partials + static_cast<size_t>(blockIdx.x) * 2 * C);
+  constexpr int NP = FUSE ? 3 : 2;
+  float4* pg = reinterpret_cast<float4*>(partials + static_cast<size_t>(blockIdx.x) * NP * C);
   pg[tid] = ag;
   pg[C / 4 + tid] = ab;
+  if constexpr (FUSE) pg[2 * (C / 4) + tid] = acs;
 }
 
 // dgamma[c] += sum_b partials[b][c];  dbeta[c] += sum_b partials[b][C + c].   block (32, 8): 32 columns, the
 // rows strided over threadIdx.y, 4 loads in flight per thread.
 __global__ void __launch_bounds__(256)
 ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, int C) {
+                     float* __restrict__ dbeta, float* __restrict__ colsum, int C, int np) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t ld = static_cast<size_t>(np) * C;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int b = threadIdx.y;
   for (; b + 24 < nblocks; b += 32) {
-    s0 += partials[static_cast<size_t>(b) * 2 * C + c];
-    s1 += partials[static_cast<size_t>(b + 8) * 2 * C + c];
-    s2 += partials[static_cast<size_t>(b + 16) * 2 * C + c];
-    s3 += partials[static_cast<size_t>(b + 24) * 2 * C + c];
+    s0 += partials[static_cast<size_t>(b) * ld + c];
+    s1 += partials[static_cast<size_t>(b + 8) * ld + c];
+    s2 += partials[static_cast<size_t>(b + 16) * ld + c];
+    s3 += partials[static_cast<size_t>(b + 24) * ld + c];
   }
-  for (; b < nblocks; b += 8) s0 += partials[static_cast<size_t>(b) * 2 * C + c];
+  for (; b < nblocks; b += 8) s0 += partials[static_cast<size_t>(b) * ld + c];
   red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (threadIdx.y == 0) {
@@ -168,7 +186,8 @@ ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, float* __r
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
     if (c < C) dgamma[c] += s;
-    else dbeta[c - C] += s;
+    else if (c < 2 * C) dbeta[c - C] += s;
+    else colsum[c - 2 * C] += s;
   }
 }
 
@@ -517,7 +536,7 @@ static int ln_bwd_grid(int M) {
 }
 // fp32 workspace elements pk_layernorm_bwd needs (per-block partial sums of dgamma / dbeta)
 extern "C" long long pk_layernorm_bwd_ws_floats(int M, int C) {
-  return static_cast<long long>(ln_bwd_grid(M)) * 2 * C;
+  return static_cast<long long>(ln_bwd_grid(M)) * 3 * C;
 }
 
 extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* mean,
@@ -526,12 +545,34 @@ extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int l
   PK_CHECK(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "pk_layernorm_bwd: null pointer");
   PK_CHECK(C % 128 == 0 && C <= 1024 && lddy % 4 == 0 && ldx % 4 == 0, "pk_layernorm_bwd: bad C=%d", C);
   const int grid = ln_bwd_grid(M);
-  ln_bwd_kernel<<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres,
-                                                                     dx, workspace, M, C);
+  ln_bwd_kernel<false><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres,
+                                                                            dx, workspace, M, C, nullptr, 0, nullptr);
   PK_LAUNCH_CHECK("pk_layernorm_bwd");
   ln_bwd_reduce_kernel<<<2 * C / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
-                                                                                        dbeta, C);
+                                                                                        dbeta, nullptr, C, 2);
   PK_LAUNCH_CHECK("pk_layernorm_bwd(reduce)");
+  return 0;
+}
+
+// pk_layernorm_bwd + pk_scale_cast_colsum of its result in one pass: additionally writes
+// dx_bf16 = bf16(rowscale[row / rows_per_group] * dx) and adds its column sums to colsum[C].
+extern "C" int pk_layernorm_bwd_cast(const float* dy, int lddy, const float* x, int ldx, const float* mean,
+                                     const float* rstd, const float* gamma, const float* dres, float* dx,
+                                     float* dgamma, float* dbeta, float* workspace, const float* rowscale,
+                                     int rows_per_group, void* dx_bf16, float* colsum, int M, int C, void* stream) {
+  PK_CHECK(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace && dx_bf16 && colsum,
+           "pk_layernorm_bwd_cast: null pointer");
+  PK_CHECK(C % 128 == 0 && C <= 1024 && lddy % 4 == 0 && ldx % 4 == 0, "pk_layernorm_bwd_cast: bad C=%d", C);
+  if (rowscale) PK_CHECK(rows_per_group > 0, "pk_layernorm_bwd_cast: rows_per_group must be > 0");
+  int grid = sm_count() * 2;   // the fused variant keeps 2 blocks per SM resident (<= ln_bwd_grid(M): workspace fits)
+  if (grid > (M + LNB_ROWS - 1) / LNB_ROWS) grid = (M + LNB_ROWS - 1) / LNB_ROWS;
+  ln_bwd_kernel<true><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
+      static_cast<__nv_bfloat16*>(dx_bf16));
+  PK_LAUNCH_CHECK("pk_layernorm_bwd_cast");
+  ln_bwd_reduce_kernel<<<3 * C / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
+                                                                                        dbeta, colsum, C, 3);
+  PK_LAUNCH_CHECK("pk_layernorm_bwd_cast(reduce)");
   return 0;
 }
 

@@ -168,9 +168,9 @@ class BlockFn(torch.autograd.Function):
         ops.colsum_bf16(dz, out=dfc1_b)
         dfc1_w = _wgrad(dz, v, out=g_fc1)
         dv = ops.gemm(dz, wfc1, trans_b=True, kind=EPI_F32)
-        dx1 = ops.layernorm_bwd(dv, x1, mean2, rstd2, n2w, dn2w, dn2b, dres=dx2)
+        # LN2 backward also emits the attention branch's incoming gradient: bf16(DropPath scale * dx1) + its column sums
+        dx1, da = ops.layernorm_bwd(dv, x1, mean2, rstd2, n2w, dn2w, dn2b, dres=dx2, cast=(drop_a, N, dproj_b))
         # ---- attention branch ----
-        da, _ = ops.scale_cast_colsum(dx1, drop_a, N, colsum_out=dproj_b)
         if ws > 0:
             da = ops.window_partition_bf16(da, Bp, h, w, ws)
             Bw = da.shape[0] // (ws * ws)

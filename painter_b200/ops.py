@@ -163,8 +163,10 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, out_dtype=torch.bfloat16, want_
     return out, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
-    """Returns dx fp32 [M, C] (+ dres); accumulates into dgamma / dbeta (fp32, caller-initialised)."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, cast=None):
+    """Returns dx fp32 [M, C] (+ dres); accumulates into dgamma / dbeta (fp32, caller-initialised).
+    cast = (rowscale or None, rows_per_group, colsum_out[C]): also returns bf16(rowscale * dx) and adds its column
+    sums to colsum_out (the fused form of `scale_cast_colsum(layernorm_bwd(...))`)."""
     _req(dy, torch.float32, "dy")
     _req(x, torch.float32, "x")
     M, C = x.shape
@@ -175,6 +177,14 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
     L = lib()
     L.pk_layernorm_bwd_ws_floats.restype = ctypes.c_longlong
     ws = torch.empty((int(L.pk_layernorm_bwd_ws_floats(M, C)),), dtype=torch.float32, device=x.device)
+    if cast is not None:
+        rowscale, rpg, cs = cast
+        dxb = torch.empty((M, C), dtype=torch.bfloat16, device=x.device)
+        check(L.pk_layernorm_bwd_cast(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd),
+                                      _ptr(gamma), _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws),
+                                      _ptr(rowscale), rpg, _ptr(dxb), _ptr(cs), M, C, _stream()),
+              "pk_layernorm_bwd_cast")
+        return dx, dxb
     check(L.pk_layernorm_bwd(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma),
                              _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), M, C, _stream()),
           "pk_layernorm_bwd")

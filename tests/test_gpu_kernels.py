@@ -137,6 +137,13 @@ def test_layernorm_fwd_bwd():
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     dx = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, dres=dres)
     assert relmax(dx, xr.grad + dres) < 2e-5 and relmax(dg, gr.grad) < 1e-4 and relmax(db, br.grad) < 1e-4
+    # fused form: also bf16(DropPath scale * dx) and its column sums (pk_layernorm_bwd_cast)
+    rs = torch.tensor([1.25, 0.0, 0.8], device=DEV)
+    dg2, db2, cs = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dx2, dxb = ops.layernorm_bwd(dy, x, mean, rstd, g, dg2, db2, dres=dres, cast=(rs, M // 3, cs))
+    want = (xr.grad + dres) * rs.repeat_interleave(M // 3)[:, None]
+    assert relmax(dx2, xr.grad + dres) < 2e-5 and relmax(dg2, gr.grad) < 1e-4 and relmax(db2, br.grad) < 1e-4
+    assert dxb.dtype == torch.bfloat16 and relmax(dxb, want) < 1e-2 and relmax(cs, want.sum(0)) < 1e-4
 
 
 def test_patch_embed_lowering_and_token_assembly():

@@ -259,10 +259,12 @@ def main():
     sync()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    # every step's inputs are copied from pinned host memory inside the timed region (the first copy is issued
-    # after e2.record()); DevicePrefetcher overlaps the copy of step i+1 with the kernels of step i
-    from painter_b200.data_utils import DevicePrefetcher
-    for batch in DevicePrefetcher((host for _ in range(args.steps)), dev):
+    # every step's inputs are copied from pinned host memory inside the timed region, on the compute stream at the
+    # top of the step exactly as engine_train.py:52-56 does (painter_b200.data_utils.DevicePrefetcher can hide the
+    # ~1.5 ms copy under the previous step, but showed intermittent multi-10-ms stalls on the GPU boxes in this
+    # synchronous loss.item()-per-step loop, so the headline number uses the plain path)
+    for _ in range(args.steps):
+        batch = [t.to(dev, non_blocking=True) for t in host]
         last_loss = step(batch, True)
     e3.record()
     sync()

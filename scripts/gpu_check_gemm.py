@@ -63,6 +63,7 @@ def run_case(name, M, N, K, ta, tb, kind, bn):
     ref = a.float() @ b.float().t()
     _lib.lib().pk_gemm_force_bn(bn)
     _lib.lib().pk_gemm_use_2cta(int(os.environ.get("PK_2CTA", "0")))
+    _lib.lib().pk_gemm_force_splits(int(os.environ.get("PK_FORCE_SPLITS", "0")))   # 0 = library heuristic
     bias = torch.randn(N, device=dev)
     kw = {}
     if kind == "bf16":

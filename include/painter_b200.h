@@ -67,6 +67,12 @@ int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, int lda, int
 /* test hooks: force the GEMM N-tile (64/128/256) or split-K factor; 0 restores the heuristics */
 void pk_gemm_force_bn(int bn);
 void pk_gemm_force_splits(int s);
+/* Host-only views of the GEMM scheduler (schedule tests; no device work).  pk_gemm_plan: out9 = {cta_pair_kernel,
+ * BN, row blocks, column blocks, splits, k-blocks per split, stream-K units per cluster, raster group, workers}.
+ * pk_gemm_plan_walk: the (row block, column block, kb0, kb1) items worker `worker` processes, 4 ints each; returns
+ * minus the item count. */
+int pk_gemm_plan(int M, int N, int K, int kind, int accumulate, int* out9);
+int pk_gemm_plan_walk(int M, int N, int K, int kind, int accumulate, int worker, int* out4, int max_items);
 /* 0 = single-CTA tiles (128 x BN), 1 = CTA pairs / cta_group::2 (256 x BN) whenever the shape allows */
 void pk_gemm_use_2cta(int on);
 

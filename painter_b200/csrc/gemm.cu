@@ -300,29 +300,11 @@ extern "C" void pk_gemm_force_bn(int bn) { pk::g_force_bn = bn; }
 extern "C" void pk_gemm_force_splits(int s) { pk::g_force_splits = s; }
 extern "C" void pk_gemm_use_2cta(int on) { pk::g_use_2cta = on; }
 
-extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, int lda, int ldb,
-                            int transA, int transB, const PkEpilogue* epi, void* stream) {
+// Tiling / scheduling decisions of one pk_gemm_bf16 call (host only; also reachable through pk_gemm_plan for the
+// CPU-side schedule tests).  Returns the kernel arguments and which kernel (CTA pair or single CTA) runs them.
+static void plan_gemm(int M, int N, int K, int transA, int transB, const PkEpilogue* epi, pk::GemmArgs& gout,
+                      bool& two_cta) {
   using namespace pk;
-  PK_CHECK(A && B && epi && epi->out, "pk_gemm_bf16: null pointer");
-  PK_CHECK(M > 0 && N > 0 && K > 0, "pk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
-  PK_CHECK(N % 64 == 0, "pk_gemm_bf16: N=%d must be a multiple of 64", N);
-  PK_CHECK(lda % 8 == 0 && ldb % 8 == 0, "pk_gemm_bf16: lda/ldb must be multiples of 8 (16 B)");
-  PK_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-           "pk_gemm_bf16: operands must be 16-byte aligned");
-  PK_CHECK(epi->kind >= PK_EPI_BF16 && epi->kind <= PK_EPI_PIXSHUF, "pk_gemm_bf16: bad epilogue %d",
-           epi->kind);
-  if (epi->kind != PK_EPI_PIXSHUF)
-    PK_CHECK(epi->ldc % 8 == 0 && epi->ldc >= N, "pk_gemm_bf16: bad ldc %d", epi->ldc);
-  if (epi->kind == PK_EPI_RESID || epi->kind == PK_EPI_DGELU)
-    PK_CHECK(epi->aux && epi->ld_aux % 8 == 0, "pk_gemm_bf16: epilogue %d needs aux", epi->kind);
-  if (epi->kind == PK_EPI_GELU) PK_CHECK(epi->out2, "pk_gemm_bf16: GELU epilogue needs out2");
-  if (epi->kind == PK_EPI_RESID && epi->rowscale)
-    PK_CHECK(epi->rows_per_group > 0, "pk_gemm_bf16: rows_per_group must be > 0");
-  if (epi->kind == PK_EPI_PIXSHUF)
-    PK_CHECK(epi->ps_c % 32 == 0 && epi->ps_h * epi->ps_w > 0 && M % (epi->ps_h * epi->ps_w) == 0 &&
-                 N == epi->ps_p * epi->ps_p * epi->ps_c,
-             "pk_gemm_bf16: bad pixel-shuffle geometry");
-
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = M;
@@ -366,7 +348,8 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
   if (g.splits == 1 && g.epi.kind == PK_EPI_F32 && g.epi.accumulate == 2) g.epi.accumulate = 1;
 
   // CTA-pair kernel (256 x BN tiles): needs a pair-tile count that can feed 74 clusters
-  if (g_use_2cta && (BN == 256 || BN == 128) && M >= 256) {
+  two_cta = g_use_2cta && (BN == 256 || BN == 128) && M >= 256;
+  if (two_cta) {
     GemmArgs g2 = g;
     g2.num_m_tiles = (M + 255) / 256;
     g2.stages = gemm_stages_for(GEMM_A_BYTES + (BN / 2) * 128);
@@ -395,8 +378,104 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
     // rasterisation: keep B L2-resident when it fits, otherwise sweep the columns inside groups of 8 row blocks
     // (stream-K calls with a large B keep the row-fastest order: measured 1006 vs 918 TF/s on the decoder wgrad)
     g2.group_m = (static_cast<long long>(N) * K * 2 <= (40ll << 20)) ? 1 : (g2.streamk_units > 0 ? 0 : 8);
-    return launch_gemm2(A, B, lda, ldb, g2, static_cast<cudaStream_t>(stream));
+    gout = g2;
+    return;
   }
+  gout = g;
+}
+
+// Host-side views of the scheduler (no device work): the plan of a call, and the (row block, column block, k-block
+// range) items one cluster / CTA walks - the same GemmSched / gemm_tile_coords code the kernels run.
+extern "C" int pk_gemm_plan(int M, int N, int K, int kind, int accumulate, int* out9) {
+  using namespace pk;
+  PK_CHECK(out9 && M > 0 && N > 0 && K > 0 && N % 64 == 0, "pk_gemm_plan: bad arguments");
+  PkEpilogue e;
+  memset(&e, 0, sizeof(e));
+  e.kind = kind;
+  e.accumulate = accumulate;
+  GemmArgs g;
+  bool two = false;
+  plan_gemm(M, N, K, 0, 0, &e, g, two);
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int tiles = g.num_m_tiles * g.num_n_tiles;
+  int workers;
+  if (two) {
+    workers = sm_count() / 2;
+    if (g.streamk_units > 0) workers = (tiles * num_kb + g.streamk_units - 1) / g.streamk_units;
+    else if (workers > tiles * g.splits) workers = tiles * g.splits;
+  } else {
+    workers = sm_count() < tiles * g.splits ? sm_count() : tiles * g.splits;
+  }
+  const int vals[9] = {two ? 1 : 0, g.BN, g.num_m_tiles, g.num_n_tiles, g.splits, g.kb_per_split, g.streamk_units,
+                       g.group_m, workers};
+  for (int i = 0; i < 9; ++i) out9[i] = vals[i];
+  return 0;
+}
+
+extern "C" int pk_gemm_plan_walk(int M, int N, int K, int kind, int accumulate, int worker, int* out4, int max_items) {
+  using namespace pk;
+  PK_CHECK(out4 && max_items > 0, "pk_gemm_plan_walk: bad arguments");
+  int plan[9];
+  if (pk_gemm_plan(M, N, K, kind, accumulate, plan)) return 2;
+  PkEpilogue e;
+  memset(&e, 0, sizeof(e));
+  e.kind = kind;
+  e.accumulate = accumulate;
+  GemmArgs g;
+  bool two = false;
+  plan_gemm(M, N, K, 0, 0, &e, g, two);
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int tiles = g.num_m_tiles * g.num_n_tiles;
+  int n = 0;
+  if (two) {
+    GemmSched sch;
+    sch.init(g, tiles, num_kb, worker, plan[8]);
+    int mn, kb0, kb1;
+    while (sch.next(mn, kb0, kb1) && n < max_items) {
+      int mb, nb;
+      gemm_tile_coords(g, mn, mb, nb);
+      out4[4 * n] = mb; out4[4 * n + 1] = nb; out4[4 * n + 2] = kb0; out4[4 * n + 3] = kb1;
+      ++n;
+    }
+  } else {
+    for (int tile = worker; tile < tiles * g.splits && n < max_items; tile += plan[8]) {
+      const int mn = tile % tiles, split = tile / tiles;
+      const int kb0 = split * g.kb_per_split;
+      const int kb1 = num_kb < kb0 + g.kb_per_split ? num_kb : kb0 + g.kb_per_split;
+      out4[4 * n] = mn % g.num_m_tiles; out4[4 * n + 1] = mn / g.num_m_tiles; out4[4 * n + 2] = kb0; out4[4 * n + 3] = kb1;
+      ++n;
+    }
+  }
+  return -n;   // number of items, negated (0 and positive values are the usual status codes)
+}
+
+extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, int lda, int ldb,
+                            int transA, int transB, const PkEpilogue* epi, void* stream) {
+  using namespace pk;
+  PK_CHECK(A && B && epi && epi->out, "pk_gemm_bf16: null pointer");
+  PK_CHECK(M > 0 && N > 0 && K > 0, "pk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  PK_CHECK(N % 64 == 0, "pk_gemm_bf16: N=%d must be a multiple of 64", N);
+  PK_CHECK(lda % 8 == 0 && ldb % 8 == 0, "pk_gemm_bf16: lda/ldb must be multiples of 8 (16 B)");
+  PK_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+           "pk_gemm_bf16: operands must be 16-byte aligned");
+  PK_CHECK(epi->kind >= PK_EPI_BF16 && epi->kind <= PK_EPI_PIXSHUF, "pk_gemm_bf16: bad epilogue %d",
+           epi->kind);
+  if (epi->kind != PK_EPI_PIXSHUF)
+    PK_CHECK(epi->ldc % 8 == 0 && epi->ldc >= N, "pk_gemm_bf16: bad ldc %d", epi->ldc);
+  if (epi->kind == PK_EPI_RESID || epi->kind == PK_EPI_DGELU)
+    PK_CHECK(epi->aux && epi->ld_aux % 8 == 0, "pk_gemm_bf16: epilogue %d needs aux", epi->kind);
+  if (epi->kind == PK_EPI_GELU) PK_CHECK(epi->out2, "pk_gemm_bf16: GELU epilogue needs out2");
+  if (epi->kind == PK_EPI_RESID && epi->rowscale)
+    PK_CHECK(epi->rows_per_group > 0, "pk_gemm_bf16: rows_per_group must be > 0");
+  if (epi->kind == PK_EPI_PIXSHUF)
+    PK_CHECK(epi->ps_c % 32 == 0 && epi->ps_h * epi->ps_w > 0 && M % (epi->ps_h * epi->ps_w) == 0 &&
+                 N == epi->ps_p * epi->ps_p * epi->ps_c,
+             "pk_gemm_bf16: bad pixel-shuffle geometry");
+
+  GemmArgs g;
+  bool two_cta = false;
+  plan_gemm(M, N, K, transA, transB, epi, g, two_cta);
+  if (two_cta) return launch_gemm2(A, B, lda, ldb, g, static_cast<cudaStream_t>(stream));
 
   CUtensorMap tmA, tmB;
   {
@@ -410,7 +489,7 @@ extern "C" int pk_gemm_bf16(const void* A, const void* B, int M, int N, int K, i
     strides[0] = static_cast<uint64_t>(lda) * 2;
     if (!make_tmap_bf16(&tmA, A, 2, dims, strides, box)) return 3;
     if (!g.transB) {
-      dims[0] = K; dims[1] = N; box[0] = 64; box[1] = static_cast<uint32_t>(BN);
+      dims[0] = K; dims[1] = N; box[0] = 64; box[1] = static_cast<uint32_t>(g.BN);
     } else {
       dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64;
     }

@@ -68,7 +68,7 @@ struct GemmArgs {
 struct GemmSched {
   int tiles_mn, num_kb, kbps, total, ncl, cur, end;
   bool sk;
-  __device__ __forceinline__ void init(const GemmArgs& g, int tiles_mn_, int num_kb_, int cid, int ncl_) {
+  __host__ __device__ __forceinline__ void init(const GemmArgs& g, int tiles_mn_, int num_kb_, int cid, int ncl_) {
     tiles_mn = tiles_mn_;
     num_kb = num_kb_;
     kbps = g.kb_per_split;
@@ -77,26 +77,26 @@ struct GemmSched {
     if (sk) {
       total = tiles_mn * num_kb;
       cur = cid * g.streamk_units;
-      end = min(total, cur + g.streamk_units);
+      end = total < cur + g.streamk_units ? total : cur + g.streamk_units;
     } else {
       total = tiles_mn * g.splits;
       cur = cid;
       end = total;
     }
   }
-  __device__ __forceinline__ bool next(int& mn, int& kb0, int& kb1) {
+  __host__ __device__ __forceinline__ bool next(int& mn, int& kb0, int& kb1) {
     if (cur >= end) return false;
     if (sk) {
       mn = cur / num_kb;
       kb0 = cur - mn * num_kb;
-      const int len = min(num_kb - kb0, end - cur);
+      const int len = (num_kb - kb0) < (end - cur) ? (num_kb - kb0) : (end - cur);
       kb1 = kb0 + len;
       cur += len;
     } else {
       mn = cur % tiles_mn;
       const int split = cur / tiles_mn;
       kb0 = split * kbps;
-      kb1 = min(num_kb, kb0 + kbps);
+      kb1 = num_kb < kb0 + kbps ? num_kb : kb0 + kbps;
       cur += ncl;
     }
     return true;
@@ -108,7 +108,7 @@ struct GemmSched {
 // (A read once; right whenever B - weights, <= 40 MB - stays L2-resident: the N = 1024 GEMMs with K = 4096 read 2.3x
 // their algorithmic bytes with row blocks fastest); larger groups bound the B re-reads when B does not fit
 // (decoder_embed: 134 MB of weights).
-__device__ __forceinline__ void gemm_tile_coords(const GemmArgs& g, int mn, int& m_blk, int& n_blk) {
+__host__ __device__ __forceinline__ void gemm_tile_coords(const GemmArgs& g, int mn, int& m_blk, int& n_blk) {
   if (g.group_m <= 0) {
     m_blk = mn % g.num_m_tiles;
     n_blk = mn / g.num_m_tiles;
@@ -116,7 +116,8 @@ __device__ __forceinline__ void gemm_tile_coords(const GemmArgs& g, int mn, int&
   }
   const int per_group = g.group_m * g.num_n_tiles;
   const int grp = mn / per_group, r = mn - grp * per_group;
-  const int gm = min(g.group_m, g.num_m_tiles - grp * g.group_m);
+  const int rem = g.num_m_tiles - grp * g.group_m;
+  const int gm = g.group_m < rem ? g.group_m : rem;
   m_blk = grp * g.group_m + r % gm;
   n_blk = r / gm;
 }

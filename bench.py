@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (N > 1)")
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "pk"],
+                    help="AdamW implementation: torch's fused multi-tensor kernel or painter_b200.optim.FusedAdamW")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="diagnostic only; the reported step includes AdamW")
@@ -191,7 +193,11 @@ def main():
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=args.bucket_mb)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, fused=True)
+    if args.optimizer == "pk":
+        from painter_b200.optim import FusedAdamW
+        opt = FusedAdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, fused=True)
 
     host = [t.pin_memory() for t in _batch(B, dist_utils.rank_seed(0, rank) % 9973)]
     resident = [t.to(dev) for t in host]
@@ -304,7 +310,9 @@ def main():
             "config": {"workload": "ViT-L 896x448 bf16 MIM train step (fwd+bwd+AdamW), batch 8 per GPU "
                                    "(BASELINE.json configs[1]; configs[3] at 8 GPUs)",
                        "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single",
-                       "tokens_per_image": 1568, "optimizer": "none" if args.no_optimizer else "AdamW(fused)",
+                       "tokens_per_image": 1568,
+                       "optimizer": "none" if args.no_optimizer else ("AdamW(painter_b200.optim.FusedAdamW)"
+                                                                      if args.optimizer == "pk" else "AdamW(fused)"),
                        "l2": "per-step working set (1.5 GB weights + >10 GB activations) far exceeds the 126 MB L2; "
                              "no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -179,6 +179,26 @@ int pk_conv3x3_dgrad_unshuffle(const void* dc1_nhwc, const void* wmat_t, void* o
 int pk_conv3x3_wgrad(const void* g_nhwc, const void* dc1_nhwc, float* out, int B, int H, int W, void* stream);
 int pk_conv3x3_wgrad_unpack(const float* acc, float* dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step: fused multi-tensor AdamW with per-tensor lr / weight decay (the groups of
+ * Painter/util/lr_decay.py:param_groups_lrd, main_train.py:344-348) and the global gradient norm of
+ * util/misc.py:252-278.  `tensors_dev`: device array of PkOptTensor; `chunks_dev`: device array of int pairs
+ * (tensor index, chunk index) - one CUDA block per chunk of pk_opt_chunk_elems() elements.  gscale (nullable device
+ * scalar) multiplies every gradient (1 / loss scale, clip coefficient); gscale_cap > 0 clamps it from above
+ * (clip coefficient min(1, .)).  pk_grad_sumsq adds sum(g^2) over all tensors to out_zeroed[0].              */
+typedef struct PkOptTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  float lr, wd;
+} PkOptTensor;
+int pk_opt_chunk_elems(void);
+int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, float beta1, float beta2,
+                  float eps, int step, const float* gscale, float gscale_cap, void* stream);
+int pk_grad_sumsq(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, float* out_zeroed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,124 @@
+"""Optimizer step on the device library.
+
+`FusedAdamW` mirrors `torch.optim.AdamW` as the reference builds it (`Painter/main_train.py:344-348`:
+`torch.optim.AdamW(param_groups, lr=args.lr, betas=(0.9, 0.999))` over `lr_decay.param_groups_lrd` groups, each with
+its own `lr` (after `lr_sched.adjust_learning_rate` multiplies by `lr_scale`) and `weight_decay`): decoupled weight
+decay, bias-corrected first/second moments, fp32 state.  One kernel launch updates every parameter
+(`pk_adamw_step`); unscaling by the AMP loss scale and gradient clipping ride along as a device-side multiplier,
+the way `util/misc.py:252-278` sequences unscale -> clip -> step, without extra passes over the gradients.
+`global_grad_norm` is `misc.get_grad_norm_` / `clip_grad_norm_`'s 2-norm in one launch (`pk_grad_sumsq`).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+_REC = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("lr", "<f4"), ("wd", "<f4")])
+assert _REC.itemsize == 48
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_CHUNK_CACHE = {}
+
+
+def _chunk_table(numels, device):
+    """int32 [nchunks, 2] = (tensor index, chunk index), one row per CUDA block; cached per list of sizes."""
+    key = (tuple(numels), str(device))
+    tab = _CHUNK_CACHE.get(key)
+    if tab is None:
+        chunk = lib().pk_opt_chunk_elems()
+        counts = np.array([(n + chunk - 1) // chunk for n in numels], dtype=np.int64)
+        ti = np.repeat(np.arange(len(numels), dtype=np.int32), counts)
+        ci = (np.arange(counts.sum(), dtype=np.int64) - np.repeat(np.cumsum(counts) - counts, counts)).astype(np.int32)
+        tab = torch.from_numpy(np.stack([ti, ci], axis=1).copy()).to(device)
+        if len(_CHUNK_CACHE) > 16:
+            _CHUNK_CACHE.clear()
+        _CHUNK_CACHE[key] = tab
+    return tab
+
+
+def _tensor_table(entries, device):
+    """entries: list of (p, g, m, v, lr, wd) fp32 contiguous CUDA tensors (m / v may be None) -> device uint8 table."""
+    rec = np.zeros(len(entries), dtype=_REC)
+    for i, (p, g, m, v, lr, wd) in enumerate(entries):
+        rec[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr() if m is not None else 0,
+                  v.data_ptr() if v is not None else 0, p.numel(), lr, wd)
+    return torch.from_numpy(rec.view(np.uint8)).to(device)
+
+
+def _check_fp32(t, what):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError(f"painter_b200.optim: {what} must be a contiguous fp32 CUDA tensor")
+
+
+def global_grad_norm(parameters):
+    """2-norm of all gradients as a 0-dim device tensor (no host sync): `misc.get_grad_norm_(params, 2.0)`."""
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return torch.zeros((), device="cuda")
+    dev = grads[0].device
+    for g in grads:
+        _check_fp32(g, "gradient")
+    table = _tensor_table([(g, g, None, None, 0.0, 0.0) for g in grads], dev)
+    chunks = _chunk_table([g.numel() for g in grads], dev)
+    out = torch.zeros(1, dtype=torch.float32, device=dev)
+    check(lib().pk_grad_sumsq(_ptr(table), _ptr(chunks), chunks.shape[0], _ptr(out), _stream()), "pk_grad_sumsq")
+    return out.sqrt_()[0]
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=None, grad_scale_cap=0.0):
+        """grad_scale: optional 1-element fp32 device tensor every gradient is multiplied by (1 / loss scale, or the
+        clip coefficient max_norm / (norm + 1e-6)); grad_scale_cap > 0 clamps it from above (clip: cap = 1)."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        # groups may differ in betas / eps / step count (they do not in the reference): one launch per such class
+        classes = {}
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    _check_fp32(p, "parameter")
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                g = p.grad
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                _check_fp32(g, "gradient")
+                key = (b1, b2, group["eps"], st["step"])
+                classes.setdefault(key, []).append((p, g, st["exp_avg"], st["exp_avg_sq"], group["lr"],
+                                                    group["weight_decay"]))
+        for (b1, b2, eps, step), entries in classes.items():
+            dev = entries[0][0].device
+            chunks = _chunk_table([e[0].numel() for e in entries], dev)
+            table = _tensor_table(entries, dev)
+            gs = None
+            if grad_scale is not None:
+                gs = grad_scale.reshape(-1)[:1]
+                _check_fp32(gs, "grad_scale")
+            check(lib().pk_adamw_step(_ptr(table), _ptr(chunks), chunks.shape[0], ctypes.c_float(b1),
+                                      ctypes.c_float(b2), ctypes.c_float(eps), step,
+                                      _ptr(gs) if gs is not None else None, ctypes.c_float(grad_scale_cap),
+                                      _stream()), "pk_adamw_step")
+        return loss

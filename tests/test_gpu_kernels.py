@@ -345,3 +345,34 @@ def test_decoder_head_loss_and_gradients(seggpt):
     dg = leaves[0].grad.permute(0, 2, 3, 1)          # NHWC
     want = dg.reshape(B, h, p, w, p, 64).permute(0, 1, 3, 2, 4, 5).reshape(B * h * w, p * p * 64)
     assert relmax(dD, want) < 3e-2
+
+
+def test_fused_adamw_and_grad_norm_match_torch():
+    """the optimizer step of main_train.py:344-348 (param groups with their own lr / weight decay)
+    and the gradient norm / clip of util/misc.py:252-278, against torch.optim.AdamW and clip_grad_norm_."""
+    from painter_b200.optim import FusedAdamW, global_grad_norm
+    torch.manual_seed(0)
+    shapes = [(1024, 1024), (3,), (111, 64), (4096,), (7, 5, 3), (16384 * 3 + 5,), (64, 64, 3, 3)]
+    ref = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+
+    def groups(ps):
+        return [{"params": ps[:3], "lr": 3e-3, "weight_decay": 0.05}, {"params": ps[3:], "lr": 1e-3, "weight_decay": 0.0}]
+
+    o_ref = torch.optim.AdamW(groups(ref), lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    o_pk = FusedAdamW(groups(ours), lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(4):
+        gs = [torch.randn(s, device=DEV) * (10.0 if step == 2 else 1.0) for s in shapes]
+        for p, q, g in zip(ref, ours, gs):
+            p.grad = g.clone()
+            q.grad = g.clone()
+        norm_ref = torch.nn.utils.clip_grad_norm_(ref, 3.0)          # clips ref's grads in place
+        norm = global_grad_norm(ours)
+        assert abs(norm.item() - norm_ref.item()) < 1e-4 * norm_ref.item()
+        coef = (3.0 / (norm + 1e-6)).reshape(1)
+        o_ref.step()
+        o_pk.step(grad_scale=coef, grad_scale_cap=1.0)
+        for p, q in zip(ref, ours):
+            assert relmax(q, p) < 2e-6, (step, tuple(p.shape))
+    for p, q in zip(ref, ours):
+        assert relmax(o_pk.state[q]["exp_avg_sq"], o_ref.state[p]["exp_avg_sq"]) < 2e-6

@@ -266,12 +266,37 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     # every step's inputs are copied from pinned host memory inside the timed region, on the compute stream at the
-    # top of the step exactly as engine_train.py:52-56 does (painter_b200.data_utils.DevicePrefetcher can hide the
-    # ~1.5 ms copy under the previous step, but showed intermittent multi-10-ms stalls on the GPU boxes in this
-    # synchronous loss.item()-per-step loop, so the headline number uses the plain path)
-    for _ in range(args.steps):
+    # top of the step exactly as engine_train.py:52-56 does, and every step's loss is read back to the host: the
+    # 4-byte D2H copy is issued asynchronously into pinned memory right after the step and consumed one step later
+    # (the last one after the loop), so the launch pipeline is not drained every step - a per-step loss.item() made
+    # this region hostage to host-side hiccups on the GPU boxes (69 -> 84-118 ms in some runs, same kernels)
+    losses = torch.empty(args.steps, dtype=torch.float32).pin_memory()
+    seen = []
+
+    def step_e2e(batch, i):
+        imgs, tgts, mask, valid = batch
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, _, _ = net(imgs, tgts, bool_masked_pos=mask, valid=valid)
+        loss.backward()
+        if not args.no_optimizer:
+            opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
+    prev = None
+    for i in range(args.steps):
         batch = [t.to(dev, non_blocking=True) for t in host]
-        last_loss = step(batch, True)
+        ev = step_e2e(batch, i)
+        if prev is not None:
+            prev[1].synchronize()
+            seen.append(float(losses[prev[0]]))
+        prev = (i, ev)
+    prev[1].synchronize()
+    seen.append(float(losses[prev[0]]))
+    last_loss = seen[-1]
     e3.record()
     sync()
     ms_e2e = e2.elapsed_time(e3)

@@ -195,8 +195,8 @@ typedef struct PkOptTensor {
   float lr, wd;
 } PkOptTensor;
 int pk_opt_chunk_elems(void);
-int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, float beta1, float beta2,
-                  float eps, int step, const float* gscale, float gscale_cap, void* stream);
+int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, double beta1, double beta2,
+                  double eps, int step, const float* gscale, float gscale_cap, void* stream);
 int pk_grad_sumsq(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, float* out_zeroed, void* stream);
 
 #ifdef __cplusplus

@@ -26,8 +26,9 @@ struct OptTensor {       // mirrors PkOptTensor (include/painter_b200.h)
 static_assert(sizeof(OptTensor) == sizeof(PkOptTensor), "PkOptTensor layout");
 
 __global__ void __launch_bounds__(256)
-adamw_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chunks, float b1, float b2, float eps,
-             float inv_bc1, float inv_sqrt_bc2, const float* __restrict__ gscale, float gscale_cap) {
+adamw_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chunks, float b1, float omb1, float b2,
+             float omb2, float eps, float inv_bc1, float inv_sqrt_bc2, const float* __restrict__ gscale,
+             float gscale_cap) {
   const int2 ck = chunks[blockIdx.x];
   const OptTensor t = tensors[ck.x];
   const long long base = static_cast<long long>(ck.y) * OPT_CHUNK;
@@ -44,8 +45,8 @@ adamw_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chu
                      reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg *= gs;
-    mm = b1 * mm + (1.f - b1) * gg;
-    vv = b2 * vv + (1.f - b2) * gg * gg;
+    mm = b1 * mm + omb1 * gg;
+    vv = b2 * vv + omb2 * gg * gg;
     pp = pp * decay - step * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
   };
   if (vec) {
@@ -102,15 +103,20 @@ sumsq_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chu
 
 extern "C" int pk_opt_chunk_elems(void) { return pk::OPT_CHUNK; }
 
-extern "C" int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, float beta1,
-                             float beta2, float eps, int step, const float* gscale, float gscale_cap, void* stream) {
+extern "C" int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, double beta1,
+                             double beta2, double eps, int step, const float* gscale, float gscale_cap,
+                             void* stream) {
   using namespace pk;
   PK_CHECK(tensors_dev && chunks_dev && nchunks > 0 && step >= 1, "pk_adamw_step: bad arguments");
-  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
-  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  // hyper-parameters arrive as doubles and 1 - beta / the bias corrections are formed in double, as torch does with
+  // its Python floats: 1.f - 0.999f is off by 1.3e-5 relative, which would show in exp_avg_sq
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   adamw_kernel<<<nchunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const OptTensor*>(tensors_dev), reinterpret_cast<const int2*>(chunks_dev), beta1, beta2, eps,
-      1.f / bc1, 1.f / sqrtf(bc2), gscale, gscale_cap);
+      reinterpret_cast<const OptTensor*>(tensors_dev), reinterpret_cast<const int2*>(chunks_dev),
+      static_cast<float>(beta1), static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
+      static_cast<float>(1.0 - beta2), static_cast<float>(eps), static_cast<float>(1.0 / bc1),
+      static_cast<float>(1.0 / sqrt(bc2)), gscale, gscale_cap);
   PK_LAUNCH_CHECK("pk_adamw_step");
   return 0;
 }

@@ -117,8 +117,8 @@ class FusedAdamW(torch.optim.Optimizer):
             if grad_scale is not None:
                 gs = grad_scale.reshape(-1)[:1]
                 _check_fp32(gs, "grad_scale")
-            check(lib().pk_adamw_step(_ptr(table), _ptr(chunks), chunks.shape[0], ctypes.c_float(b1),
-                                      ctypes.c_float(b2), ctypes.c_float(eps), step,
+            check(lib().pk_adamw_step(_ptr(table), _ptr(chunks), chunks.shape[0], ctypes.c_double(b1),
+                                      ctypes.c_double(b2), ctypes.c_double(eps), step,
                                       _ptr(gs) if gs is not None else None, ctypes.c_float(grad_scale_cap),
                                       _stream()), "pk_adamw_step")
         return loss

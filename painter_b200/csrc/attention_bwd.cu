@@ -64,7 +64,8 @@ struct AttnBwdArgs {
   __nv_bfloat16* dqkv;       // [B*N, 3C]
   float* dt_ws;              // [CTAs of kernel A][2h-1 + 2W-1][64] fp32 partial table gradients
   long long* trace;          // optional debug timeline of CTA (0,0,0): [kernel][role][iter][event]
-  int debug;                 // bit 0: disable the software pipelining of kernel A (bring-up aid)
+  int debug;                 // measurement aids: bit 1 trace the last (b, head) CTA instead of the first,
+                             // bit 2 skip kernel A, bit 3 skip kernel B (scripts/time_attn_parts.py)
   int kv_stages;             // kernel A: K/V ring depth (3 normally; 2 when shared memory is short)
 };
 

@@ -63,6 +63,22 @@ def test_painter_tiny_eval_and_train():
     assert _rel(pred, it["pred"]) < 2e-5
 
 
+def test_painter_tiny_other_loss_functions():
+    """models_painter.py:453-458: loss_func in {l1, l2, l1l2} (smoothl1 is the stock one, covered above)."""
+    gold = _load("painter_tiny_losses.pt")
+    assert [c["cfg"]["loss_func"] for c in gold["cases"]] == ["l1", "l2", "l1l2"]
+    for c in gold["cases"]:
+        cfg = po.PainterConfig(**c["cfg"])
+        sd = synth_state_dict(cfg, c["weight_seed"])
+        imgs, tgts, mask, valid = synth_inputs(cfg, **c["inputs"])
+        loss, _, _, g = _oracle_run(cfg, sd, imgs, tgts, mask, valid)
+        assert abs(loss.item() - c["loss"].item()) < 2e-6 * abs(c["loss"].item()), cfg.loss_func
+        for k, ref in c["grads"].items():
+            assert _rel(g[k], ref) < 2e-4, (cfg.loss_func, k)
+        for k, n in c["grad_norms"].items():
+            assert abs(g[k].norm().item() - n) <= 2e-4 * max(n, 1e-6), (cfg.loss_func, k)
+
+
 def test_painter_tiny_window():
     gold = _load("painter_tiny_window.pt")
     cfg = po.PainterConfig(**gold["cfg"])

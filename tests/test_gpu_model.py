@@ -195,3 +195,19 @@ def test_device_prefetcher_yields_every_pinned_batch_once():
         assert a.is_cuda and b.is_cuda
         seen.append((a.sum().item(), b[0].item()))
     assert seen == [(64.0 * 64 * i, i) for i in range(5)]
+
+
+def test_painter_tiny_other_loss_functions_vs_reference_golden():
+    """loss_func in {l1, l2, l1l2} (models_painter.py:453-458; non-stock): forward loss and the gradients that flow
+    through the fused decoder head, against vectors produced by the unmodified reference."""
+    gold = load_golden("painter_tiny_losses.pt")
+    for c in gold["cases"]:
+        cfg = po.PainterConfig(**c["cfg"])
+        model, sd = build_model(cfg, c["weight_seed"])
+        model.eval()
+        imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, **c["inputs"]))
+        loss, _, _ = model(imgs, tgts, mask, valid)
+        assert abs(loss.item() - c["loss"].item()) <= LOSS_TOL * abs(c["loss"].item()), cfg.loss_func
+        loss.backward()
+        noise, _ = _reference_bf16_noise(cfg, sd, imgs, tgts, mask, valid)
+        _check_grads(model, c["grads"], c["grad_norms"], noise)

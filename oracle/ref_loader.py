@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE: import the UNMODIFIED reference modules from /root/reference through the shim
-packages in oracle/shims (timm 0.3.2 symbols, import-only detectron2/fairscale/fvcore, torch._six).
+"""TEST INFRASTRUCTURE: import the UNMODIFIED reference modules through the shim packages in oracle/shims
+(timm 0.3.2 symbols, import-only detectron2/fairscale/fvcore, torch._six).
 
-Only usable where /root/reference exists (the authoring container).  Nothing in the product path, the
--m gpu tests, smoke() or bench.py imports this file.
+The reference tree is looked up at $PAINTER_REFERENCE, then /root/reference (the authoring container), then the
+staged byte-for-byte copy under baseline/_ref/ (scripts/stage_reference.py; git-ignored, travels to the GPU box with
+the gpurun snapshot).  Nothing in the product path (painter_b200/*) imports this file: only tests/, the
+`--impl reference` / cpu_baseline legs of bench.py and scripts under scripts/ do.
 """
 import importlib
 import importlib.util
@@ -10,8 +12,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PAINTER_REFERENCE", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "shims")
+_STAGED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _find_root():
+    for cand in (os.environ.get("PAINTER_REFERENCE"), "/root/reference", _STAGED):
+        if cand and os.path.isdir(os.path.join(cand, "Painter")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():
@@ -70,3 +83,71 @@ def masking_generator():
         d = os.path.join(REF_ROOT, "Painter")
         _cache["m"] = _load("ref_masking_generator", os.path.join(d, "util", "masking_generator.py"), d)
     return _cache["m"]
+
+
+def engine_train():
+    """Painter/engine_train.py (train_one_epoch, evaluate_pt) with its own `util.misc` / `util.lr_sched`."""
+    if "e" not in _cache:
+        d = os.path.join(REF_ROOT, "Painter")
+        _cache["e"] = _load("ref_engine_train", os.path.join(d, "engine_train.py"), d)
+    return _cache["e"]
+
+
+def misc():
+    """Painter/util/misc.py as imported by engine_train (NativeScalerWithGradNormCount, save_model, ...)."""
+    engine_train()
+    return sys.modules["_ref_ref_engine_train.util.misc"]
+
+
+def lr_decay():
+    if "ld" not in _cache:
+        d = os.path.join(REF_ROOT, "Painter")
+        _cache["ld"] = _load("ref_lr_decay", os.path.join(d, "util", "lr_decay.py"), d)
+    return _cache["ld"]
+
+
+def seggpt_engine():
+    """SegGPT/SegGPT_inference/seggpt_engine.py (run_one_image, inference_image, inference_video)."""
+    if "se" not in _cache:
+        d = os.path.join(REF_ROOT, "SegGPT", "SegGPT_inference")
+        _cache["se"] = _load("ref_seggpt_engine", os.path.join(d, "seggpt_engine.py"), d)
+    return _cache["se"]
+
+
+def painter_inference_segm():
+    """Painter/eval/ade20k_semantic/painter_inference_segm.py (run_one_image :67-93)."""
+    if "pi" not in _cache:
+        d = os.path.join(REF_ROOT, "Painter")
+        # the script imports matplotlib.pyplot (unused by run_one_image; absent from this image) and its sibling
+        # `models_painter` by bare name: both are provided for the duration of the import only
+        injected = []
+        try:
+            import matplotlib.pyplot  # noqa: F401
+        except Exception:
+            for n in ("matplotlib", "matplotlib.pyplot"):
+                sys.modules[n] = types.ModuleType(n)
+                injected.append(n)
+        had_mp = sys.modules.get("models_painter")
+        sys.modules["models_painter"] = models_painter()
+        try:
+            _cache["pi"] = _load("ref_painter_inference_segm",
+                                 os.path.join(d, "eval", "ade20k_semantic", "painter_inference_segm.py"), d)
+        finally:
+            for n in injected:
+                sys.modules.pop(n, None)
+            if had_mp is None:
+                sys.modules.pop("models_painter", None)
+            else:
+                sys.modules["models_painter"] = had_mp
+    return _cache["pi"]
+
+
+def pairdataset():
+    if "pd" not in _cache:
+        d = os.path.join(REF_ROOT, "Painter")
+        _cache["pd"] = _load("ref_pairdataset", os.path.join(d, "data", "pairdataset.py"), d)
+    return _cache["pd"]
+
+
+def examples_dir():
+    return os.path.join(REF_ROOT, "SegGPT", "SegGPT_inference", "examples")

@@ -99,6 +99,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 if not st:
                     _check_fp32(p, "parameter")
                     st["step"] = 0
+                elif torch.is_tensor(st["step"]):     # state loaded from a torch.optim.AdamW checkpoint (misc.load_model)
+                    st["step"] = int(st["step"].item())
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
@@ -121,4 +123,8 @@ class FusedAdamW(torch.optim.Optimizer):
                                       ctypes.c_double(b2), ctypes.c_double(eps), step,
                                       _ptr(gs) if gs is not None else None, ctypes.c_float(grad_scale_cap),
                                       _stream()), "pk_adamw_step")
+            # the kernel wrote through raw pointers: tell autograd (and engine.bf16_weight's (version, storage) cache
+            # key) that the parameters changed, as an in-place torch op would
+            for e in entries:
+                torch.autograd.graph.increment_version(e[0])
         return loss

@@ -1,7 +1,10 @@
 """GPU parity of the painter_b200 modules against (i) golden vectors produced by the UNMODIFIED reference and
 (ii) the CPU oracle.  Tolerances (bf16 tensor-core operands, fp32 accumulate; SURVEY.md section 8c calibration:
 the reference's own bf16-vs-fp32 noise is loss 4e-7, logits RMS 9.5e-3 / max 1.3e-2, grads RMS 1.1e-2):
-   loss   rel <= 2e-3        logits  rms-rel <= 1.5e-2, max-rel <= 4e-2        grads  rms-rel <= 4e-2
+   loss   rel <= 1e-3 (north star)     logits  rms-rel <= 1.5e-2, max-rel <= 4e-2
+   grads  rms-rel <= 1.5 x the reference's own bf16-autocast error on the same inputs, per tensor; the
+          fixed 4e-2 bound is only used where no noise measurement is available.
+The same protocol at the benchmarked shapes, against the live reference, is in tests/test_gpu_fullsize.py.
 """
 import pytest
 import torch
@@ -13,7 +16,8 @@ from _common import build_model, load_golden, rel_max, rel_rms
 
 pytestmark = pytest.mark.gpu
 
-LOSS_TOL, LOGIT_RMS, LOGIT_MAX, GRAD_RMS = 2e-3, 1.5e-2, 4e-2, 4e-2
+LOSS_TOL, LOGIT_RMS, LOGIT_MAX, GRAD_RMS = 1e-3, 1.5e-2, 4e-2, 4e-2
+NOISE_RATIO = 1.5
 
 
 def _to(dev, *ts):
@@ -38,9 +42,7 @@ def _check_grads(model, ref_grads, ref_norms=None, noise=None):
     bad = []
     for k, g in ref_grads.items():
         e = rel_rms(named[k].grad, g)
-        tol = GRAD_RMS
-        if noise is not None:
-            tol = max(tol, 1.5 * rel_rms(noise[k], g))
+        tol = GRAD_RMS if noise is None else NOISE_RATIO * rel_rms(noise[k], g)
         if e > tol:
             bad.append((k, e, tol))
     if ref_norms is not None:
@@ -211,3 +213,28 @@ def test_painter_tiny_other_loss_functions_vs_reference_golden():
         loss.backward()
         noise, _ = _reference_bf16_noise(cfg, sd, imgs, tgts, mask, valid)
         _check_grads(model, c["grads"], c["grad_norms"], noise)
+
+
+def test_fused_adamw_trains_the_gemm_weights():
+    """FusedAdamW writes parameters through raw pointers; the bf16 GEMM-weight cache of
+    engine.bf16_weight must see every update (version bump) - the loss must fall and the cached bf16 copy must equal
+    the fp32 master after each step."""
+    from painter_b200 import engine
+    from painter_b200.optim import FusedAdamW
+    cfg = po.PainterConfig(img_size=(128, 64), embed_dim=128, num_heads=2, decoder_embed_dim=64)
+    model, _ = build_model(cfg, 0)
+    model.train()
+    opt = FusedAdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.05)
+    imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, 4, 3))
+    losses = []
+    w = model.blocks[5].mlp.fc1.weight
+    for step in range(6):
+        loss, _, _ = model(imgs, tgts, bool_masked_pos=mask, valid=valid)
+        losses.append(loss.item())
+        loss.backward()
+        before = w.detach().clone()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        assert not torch.equal(before, w.detach()), "parameter did not move"
+        assert torch.equal(engine.bf16_weight(w), w.detach().bfloat16()), "stale bf16 weight cache after the step"
+    assert losses[-1] < losses[0], losses

@@ -100,29 +100,50 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_step_time(threads, reps=1, budget_s=None, min_reps=1):
-    """Oracle port (torch-CPU fp32 restatement of the reference), B=1 896x448 train step (fwd + bwd).
-    With `budget_s` the loop stops early once that much wall time is spent (after at least `min_reps` steps), so the
-    CPU legs stay bounded whatever --steps is."""
+def cpu_reference_step_time(threads, reps=1, budget_s=None, min_reps=1):
+    """The reference's own CPU path: the UNMODIFIED `models_painter.painter_vit_large_patch16_input896x448_win_dec64_
+    8glb_sl1()` module (staged copy under baseline/_ref, scripts/stage_reference.py; loaded through oracle/ref_loader)
+    in torch-CPU eager fp32, train mode, B=1 896x448 forward + backward on `threads` host threads.  Falls back to the
+    oracle port (kind "port") only if the staged tree is missing.  With `budget_s` the loop stops early once that much
+    wall time is spent (after at least `min_reps` steps), so the CPU legs stay bounded whatever --steps is.
+    Returns (times, kind)."""
     import torch
     from oracle import painter_oracle as po
+    from oracle import ref_loader
     from oracle.synth import synth_state_dict
     torch.set_num_threads(threads)
     cfg = po.PainterConfig()
-    sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(cfg, 0).items()}
     imgs, tgts, mask, valid = _batch(1, 0)
     times = []
+    if ref_loader.available():
+        kind = "reference"
+        torch.manual_seed(0)
+        model = ref_loader.models_painter().painter_vit_large_patch16_input896x448_win_dec64_8glb_sl1()
+        model.load_state_dict(synth_state_dict(cfg, 0), strict=True)
+        model.train()
+
+        def one():
+            for p in model.parameters():
+                p.grad = None
+            loss, _, _ = model(imgs, tgts, bool_masked_pos=mask, valid=valid.clone())
+            loss.backward()
+    else:
+        kind = "port"
+        sd = {k: v.requires_grad_(True) for k, v in synth_state_dict(cfg, 0).items()}
+
+        def one():
+            for v in sd.values():
+                v.grad = None
+            drops = po.draw_drop_scales(cfg, 1)
+            loss, _, _ = po.forward(sd, cfg, imgs, tgts, mask, valid, drops=drops)
+            loss.backward()
     for _ in range(reps):
-        for v in sd.values():
-            v.grad = None
         t0 = time.perf_counter()
-        drops = po.draw_drop_scales(cfg, 1)
-        loss, _, _ = po.forward(sd, cfg, imgs, tgts, mask, valid, drops=drops)
-        loss.backward()
+        one()
         times.append(time.perf_counter() - t0)
         if budget_s is not None and len(times) >= min_reps and sum(times) > budget_s:
             break
-    return times
+    return times, kind
 
 
 def run_reference(args):
@@ -131,7 +152,8 @@ def run_reference(args):
         return
     threads = min(os.cpu_count() or 1, 32)   # beyond ~32 threads torch-CPU eager slows down (oversubscription)
     # bounded sample: one warm-up step, then up to --steps timed steps or ~150 s of CPU work, whichever comes first
-    t = cpu_port_step_time(threads, reps=1 + args.steps, budget_s=150.0, min_reps=2)[1:]
+    t, kind = cpu_reference_step_time(threads, reps=1 + args.steps, budget_s=150.0, min_reps=2)
+    t = t[1:]
     ms = 1e3 * sum(t) / len(t)
     val = 1.0 / (ms / 1e3)
     line = {
@@ -140,8 +162,10 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ViT-L 896x448 MIM train step (fwd+bwd), B=1 per step on host cores",
                    "global_batch": 1, "parallelism": "cpu"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{len(t)} x (B=1 forward+backward) of the oracle port, torch-CPU fp32, after 1 warm-up"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"{len(t)} x (B=1 train-mode forward+backward) of the "
+                                   f"{'unmodified reference module' if kind == 'reference' else 'oracle port'}, "
+                                   "torch-CPU eager fp32, after 1 warm-up"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,8 +181,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size (N > 1)")
-    ap.add_argument("--optimizer", default="torch", choices=["torch", "pk"],
-                    help="AdamW implementation: torch's fused multi-tensor kernel or painter_b200.optim.FusedAdamW")
+    ap.add_argument("--optimizer", default="pk", choices=["torch", "pk"],
+                    help="AdamW implementation: painter_b200.optim.FusedAdamW (default) or torch's fused kernel")
+    ap.add_argument("--dp", default="own", choices=["own", "ddp"],
+                    help="N > 1: painter_b200.dist_utils.GradSync (bucketed all-reduce of the gradient arena issued "
+                         "from backward; default) or stock DistributedDataParallel")
+    ap.add_argument("--sm-reserve", type=int, default=8,
+                    help="N > 1, --dp own: SMs left to NCCL while gradient buckets are in flight")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="diagnostic only; the reported step includes AdamW")
@@ -191,13 +220,21 @@ def main():
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=args.bucket_mb)
+        if args.dp == "own":
+            gsync = dist_utils.GradSync(model, bucket_mb=args.bucket_mb if args.bucket_mb > 25 else 200,
+                                        sm_reserve=args.sm_reserve)
+        else:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                            bucket_cap_mb=args.bucket_mb)
+    # the reference recipe (train_painter_vit_large.sh / main_train.py:344-348): AdamW over layer-decay groups
+    from painter_b200.train_utils import adjust_learning_rate, param_groups_lrd
+    groups = param_groups_lrd(model, 0.05, no_weight_decay_list=model.no_weight_decay(), layer_decay=0.8)
     if args.optimizer == "pk":
         from painter_b200.optim import FusedAdamW
-        opt = FusedAdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05)
+        opt = FusedAdamW(groups, lr=1e-4, betas=(0.9, 0.999))
     else:
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, fused=True)
+        opt = torch.optim.AdamW(groups, lr=1e-4, betas=(0.9, 0.999), fused=True)
+    adjust_learning_rate(opt, 1.0, 1e-4, 0.0, 1, 15)
 
     host = [t.pin_memory() for t in _batch(B, dist_utils.rank_seed(0, rank) % 9973)]
     resident = [t.to(dev) for t in host]
@@ -260,49 +297,53 @@ def main():
     launches = _lib.launch_count() - n0
     record["on"] = False
     ms_total = e0.elapsed_time(e1)
-    # ---------------- timed region 2: end to end (pinned host -> device every step, loss read back) ----------------
-    last_loss = None
-    losses = torch.empty(args.steps, dtype=torch.float32).pin_memory()   # host landing zone of the per-step loss reads
-    sync()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    # every step's inputs are copied from pinned host memory inside the timed region, on the compute stream at the
-    # top of the step exactly as engine_train.py:52-56 does, and every step's loss is read back to the host: the
-    # 4-byte D2H copy is issued asynchronously into pinned memory right after the step and consumed one step later
-    # (the last one after the loop), so the launch pipeline is not drained every step - a per-step loss.item() made
-    # this region hostage to host-side hiccups on the GPU boxes (69 -> 84-118 ms in some runs, same kernels)
-    seen = []
+    # ---------------- timed region 2: end to end through the public API, the reference loop's way ----------------
+    # Every step: the batch comes from pinned host memory (painter_b200.data_utils.DevicePrefetcher issues the same
+    # .to(device, non_blocking=True) copies as engine_train.py:60-63, one step ahead on a side stream), the module is
+    # called under autocast, `loss.item()` reads the loss back and the step ends with torch.cuda.synchronize(), exactly
+    # like engine_train.py:65-93.  A second, pipelined variant (loss read deferred by one step) is reported next to it.
+    from painter_b200.data_utils import DevicePrefetcher
 
-    def step_e2e(batch, i):
-        imgs, tgts, mask, valid = batch
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss, _, _ = net(imgs, tgts, bool_masked_pos=mask, valid=valid)
-        loss.backward()
-        if not args.no_optimizer:
-            opt.step()
-        opt.zero_grad(set_to_none=True)
-        losses[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        return ev
-
-    prev = None
-    for i in range(args.steps):
-        batch = [t.to(dev, non_blocking=True) for t in host]
-        ev = step_e2e(batch, i)
+    def run_e2e(strict):
+        seen = []
+        losses = torch.empty(args.steps, dtype=torch.float32).pin_memory()
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        prev = None
+        for i, batch in enumerate(DevicePrefetcher((host for _ in range(args.steps)), dev)):
+            imgs, tgts, mask, valid = batch
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss, _, _ = net(imgs, tgts, bool_masked_pos=mask, valid=valid)
+            if strict:
+                seen.append(loss.item())                      # engine_train.py:68
+            loss.backward()
+            if not args.no_optimizer:
+                opt.step()
+            opt.zero_grad(set_to_none=True)
+            if strict:
+                torch.cuda.synchronize()                      # engine_train.py:93
+            else:
+                losses[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if prev is not None:
+                    prev[1].synchronize()
+                    seen.append(float(losses[prev[0]]))
+                prev = (i, ev)
         if prev is not None:
             prev[1].synchronize()
             seen.append(float(losses[prev[0]]))
-        prev = (i, ev)
-    prev[1].synchronize()
-    seen.append(float(losses[prev[0]]))
+        b.record()
+        sync()
+        return a.elapsed_time(b), seen
+
+    ms_e2e, seen = run_e2e(True)
+    ms_e2e_pipe, _ = run_e2e(False)
     last_loss = seen[-1]
-    e3.record()
-    sync()
-    ms_e2e = e2.elapsed_time(e3)
     clk = clocks.stop() if rank == 0 else None
 
-    ms_total, ms_e2e = dist_utils.max_over_ranks([ms_total, ms_e2e], device=dev)   # slowest rank
+    ms_total, ms_e2e, ms_e2e_pipe = dist_utils.max_over_ranks([ms_total, ms_e2e, ms_e2e_pipe], device=dev)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
     e2e_val = world * B / (ms_e2e / args.steps / 1e3)
@@ -336,12 +377,20 @@ def main():
                                    "(BASELINE.json configs[1]; configs[3] at 8 GPUs)",
                        "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single",
                        "tokens_per_image": 1568,
-                       "optimizer": "none" if args.no_optimizer else ("AdamW(painter_b200.optim.FusedAdamW)"
-                                                                      if args.optimizer == "pk" else "AdamW(fused)"),
+                       "optimizer": "none" if args.no_optimizer else (
+                           "AdamW over lr_decay.param_groups_lrd groups (layer_decay 0.8, wd 0.05): " +
+                           ("painter_b200.optim.FusedAdamW" if args.optimizer == "pk" else "torch fused AdamW")),
+                       "data_parallel": "single" if world == 1 else (
+                           "painter_b200.dist_utils.GradSync (arena buckets, NCCL all-reduce from backward)"
+                           if args.dp == "own" else "torch DistributedDataParallel"),
                        "l2": "per-step working set (1.5 GB weights + >10 GB activations) far exceeds the 126 MB L2; "
                              "no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "loop": "engine_train.train_one_epoch's: pinned-host batch -> device every step (prefetched one "
+                            "step ahead on a side stream), loss.item() and torch.cuda.synchronize() every step",
+                    "pipelined_value": world * B / (ms_e2e_pipe / args.steps / 1e3),
+                    "pipelined_note": "same, but each step's loss is read back one step later (no per-step drain)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "pk::gemm_bf16_kernel (tcgen05 GEMM, all linear layers fwd/bwd)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -353,9 +402,12 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 32)
-            ts = cpu_port_step_time(threads, reps=1)
-            line["cpu_baseline"] = {"value": 1.0 / ts[-1], "unit": "images/s", "cores": threads, "kind": "port",
-                                    "sample": "1 x (B=1 forward+backward) of the oracle port, torch-CPU fp32"}
+            ts, kind = cpu_reference_step_time(threads, reps=2)
+            line["cpu_baseline"] = {"value": 1.0 / ts[-1], "unit": "images/s", "cores": threads, "kind": kind,
+                                    "sample": "1 x (B=1 train-mode forward+backward) of the unmodified reference "
+                                              "module, torch-CPU eager fp32, after 1 warm-up"
+                                    if kind == "reference" else
+                                    "1 x (B=1 forward+backward) of the oracle port, torch-CPU fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -185,19 +185,31 @@ int pk_conv3x3_wgrad_unpack(const float* acc, float* dw, void* stream);
  * util/misc.py:252-278.  `tensors_dev`: device array of PkOptTensor; `chunks_dev`: device array of int pairs
  * (tensor index, chunk index) - one CUDA block per chunk of pk_opt_chunk_elems() elements.  gscale (nullable device
  * scalar) multiplies every gradient (1 / loss scale, clip coefficient); gscale_cap > 0 clamps it from above
- * (clip coefficient min(1, .)).  pk_grad_sumsq adds sum(g^2) over all tensors to out_zeroed[0].              */
+ * (clip coefficient min(1, .)).  pk_grad_sumsq adds sum(g^2) over all tensors to out_zeroed[0].
+ * pk_droppath_scales: timm DropPath (0.3.2 layers/drop.py; models_painter.py:199,229-230) for a whole step in one
+ * launch: out[i] = floor(round_to_dtype(keep[i] + r[i])) / keep[i], r = the torch.rand draws (dtype code 0 fp32,
+ * 1 bf16, 2 fp16: the reference adds in the branch output's dtype).                                             */
 typedef struct PkOptTensor {
   float* p;
-  const float* g;
+  float* g;
   float* m;
   float* v;
+  void* w16;      /* optional bf16 copy of p refreshed by the step (the tensor-core operand), or NULL */
   long long n;
   float lr, wd;
 } PkOptTensor;
 int pk_opt_chunk_elems(void);
+/* zero_grad != 0: every gradient element is overwritten with 0 after it has been consumed (the flat gradient
+ * arena is left clean for the next backward); found_inf (nullable device scalar): non-zero => the whole step is a
+ * no-op (torch.cuda.amp.GradScaler.step semantics, util/misc.py:266). */
 int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, double beta1, double beta2,
-                  double eps, int step, const float* gscale, float gscale_cap, void* stream);
+                  double eps, int step, const float* gscale, float gscale_cap, int zero_grad,
+                  const float* found_inf, void* stream);
 int pk_grad_sumsq(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, float* out_zeroed, void* stream);
+int pk_droppath_scales(const void* r, int dtype_code, const float* keep, float* out, int n, void* stream);
+/* Persistent kernels (the tcgen05 GEMMs) use at most `n` SMs (0 = all): leaves room for a concurrent NCCL kernel
+ * so that statically partitioned tiles never run as a second wave (multi-GPU backward).  Returns the old value. */
+int pk_set_sm_budget(int n);
 
 #ifdef __cplusplus
 }

@@ -17,15 +17,22 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<int> g_sm_budget{0};
+
+// SM count of the CURRENT device (cached per device ordinal), capped by pk_set_sm_budget and kept even (CTA pairs).
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
   }
-  return n;
+  const int b = g_sm_budget.load(std::memory_order_relaxed);
+  if (b > 0 && b < n) n = b & ~1;
+  return n < 2 ? 2 : n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -84,4 +91,5 @@ extern "C" {
 int pk_version(void) { return 100; }
 const char* pk_last_error(void) { return pk::g_err; }
 long long pk_launch_count(void) { return pk::g_launches.load(); }
+int pk_set_sm_budget(int n) { return pk::g_sm_budget.exchange(n < 0 ? 0 : n); }
 }

@@ -7,6 +7,7 @@
 //     p <- p - (lr / (1 - b1^t)) m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 // The gradient may carry a device-side multiplier (1 / loss scale, and/or the clip coefficient), so unscale + clip +
 // step are ONE pass over p, g, m, v: 7 fp32 streams, HBM-bound (10.4 GB per step for the 370.7 M parameters).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/painter_b200.h"
@@ -17,9 +18,10 @@ constexpr int OPT_CHUNK = 16384;   // elements per block: 256 threads x 16 float
 
 struct OptTensor {       // mirrors PkOptTensor (include/painter_b200.h)
   float* p;
-  const float* g;
+  float* g;
   float* m;
   float* v;
+  __nv_bfloat16* w16;    // optional bf16 copy of the updated parameter (the GEMM / attention operand), or null
   long long n;
   float lr, wd;
 };
@@ -28,7 +30,8 @@ static_assert(sizeof(OptTensor) == sizeof(PkOptTensor), "PkOptTensor layout");
 __global__ void __launch_bounds__(256)
 adamw_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chunks, float b1, float omb1, float b2,
              float omb2, float eps, float inv_bc1, float inv_sqrt_bc2, const float* __restrict__ gscale,
-             float gscale_cap) {
+             float gscale_cap, int zero_grad, const float* __restrict__ found_inf) {
+  if (found_inf && found_inf[0] != 0.f) return;   // GradScaler semantics: an overflowed step is skipped entirely
   const int2 ck = chunks[blockIdx.x];
   const OptTensor t = tensors[ck.x];
   const long long base = static_cast<long long>(ck.y) * OPT_CHUNK;
@@ -38,11 +41,13 @@ adamw_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chu
   if (gscale_cap > 0.f && gs > gscale_cap) gs = gscale_cap;   // clip coefficient: min(1, max_norm / (norm + 1e-6))
   const float decay = 1.f - t.lr * t.wd, step = t.lr * inv_bc1;
   float* p = t.p + base;
-  const float* g = t.g + base;
+  float* g = t.g + base;
   float* m = t.m + base;
   float* v = t.v + base;
+  __nv_bfloat16* w16 = t.w16 ? t.w16 + base : nullptr;
   const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
-                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(w16) & 7) == 0;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg *= gs;
     mm = b1 * mm + omb1 * gg;
@@ -60,10 +65,25 @@ adamw_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chu
       reinterpret_cast<float4*>(p)[i] = pp;
       reinterpret_cast<float4*>(m)[i] = mm;
       reinterpret_cast<float4*>(v)[i] = vv;
+      if (w16) {
+        uint2 u;
+        u.x = pack_bf16x2(pp.x, pp.y);
+        u.y = pack_bf16x2(pp.z, pp.w);
+        reinterpret_cast<uint2*>(w16)[i] = u;
+      }
+      if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += 256) upd(p[i], g[i], m[i], v[i]);
+    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += 256) {
+      upd(p[i], g[i], m[i], v[i]);
+      if (w16) w16[i] = __float2bfloat16_rn(p[i]);
+      if (zero_grad) g[i] = 0.f;
+    }
   } else {
-    for (int i = threadIdx.x; i < cnt; i += 256) upd(p[i], g[i], m[i], v[i]);
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      upd(p[i], g[i], m[i], v[i]);
+      if (w16) w16[i] = __float2bfloat16_rn(p[i]);
+      if (zero_grad) g[i] = 0.f;
+    }
   }
 }
 
@@ -105,7 +125,7 @@ extern "C" int pk_opt_chunk_elems(void) { return pk::OPT_CHUNK; }
 
 extern "C" int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, double beta1,
                              double beta2, double eps, int step, const float* gscale, float gscale_cap,
-                             void* stream) {
+                             int zero_grad, const float* found_inf, void* stream) {
   using namespace pk;
   PK_CHECK(tensors_dev && chunks_dev && nchunks > 0 && step >= 1, "pk_adamw_step: bad arguments");
   // hyper-parameters arrive as doubles and 1 - beta / the bias corrections are formed in double, as torch does with
@@ -116,7 +136,7 @@ extern "C" int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_d
       reinterpret_cast<const OptTensor*>(tensors_dev), reinterpret_cast<const int2*>(chunks_dev),
       static_cast<float>(beta1), static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
       static_cast<float>(1.0 - beta2), static_cast<float>(eps), static_cast<float>(1.0 / bc1),
-      static_cast<float>(1.0 / sqrt(bc2)), gscale, gscale_cap);
+      static_cast<float>(1.0 / sqrt(bc2)), gscale, gscale_cap, zero_grad, found_inf);
   PK_LAUNCH_CHECK("pk_adamw_step");
   return 0;
 }
@@ -128,5 +148,34 @@ extern "C" int pk_grad_sumsq(const PkOptTensor* tensors_dev, const int* chunks_d
   sumsq_kernel<<<nchunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const OptTensor*>(tensors_dev), reinterpret_cast<const int2*>(chunks_dev), out_zeroed);
   PK_LAUNCH_CHECK("pk_grad_sumsq");
+  return 0;
+}
+
+namespace pk {
+__global__ void droppath_scales_kernel(const void* __restrict__ r, int dtype_code, const float* __restrict__ keep,
+                                       float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float k = keep[i];
+  float v;
+  if (dtype_code == 1) {
+    v = k + __bfloat162float(static_cast<const __nv_bfloat16*>(r)[i]);
+    v = __bfloat162float(__float2bfloat16_rn(v));
+  } else if (dtype_code == 2) {
+    v = k + __half2float(static_cast<const __half*>(r)[i]);
+    v = __half2float(__float2half_rn(v));
+  } else {
+    v = k + static_cast<const float*>(r)[i];
+  }
+  out[i] = floorf(v) / k;
+}
+}  // namespace pk
+
+extern "C" int pk_droppath_scales(const void* r, int dtype_code, const float* keep, float* out, int n,
+                                  void* stream) {
+  PK_CHECK(r && keep && out && n > 0 && dtype_code >= 0 && dtype_code <= 2, "pk_droppath_scales: bad arguments");
+  pk::droppath_scales_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(r, dtype_code, keep,
+                                                                                              out, n);
+  PK_LAUNCH_CHECK("pk_droppath_scales");
   return 0;
 }

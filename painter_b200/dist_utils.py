@@ -26,6 +26,93 @@ def max_over_ranks(values, device=None):
     return t.tolist()
 
 
+class GradSync:
+    """Data-parallel gradient averaging for a painter_b200 module: replaces the DistributedDataParallel reducer of
+    Painter/main_train.py:340.
+
+    The module's backward stages write every gradient into the flat arena (painter_b200/arena.py) in production
+    order; as soon as the stages of a bucket (a contiguous arena range of >= bucket_mb) have been enqueued, ONE
+    all-reduce(mean) of that range is issued asynchronously (NCCL runs it on its own stream after the producing
+    kernels, over NVLink / NVSwitch), so communication overlaps the rest of backward with no copy into separate
+    buckets and a handful of large collectives per step.  The last stage waits for all of them.  While collectives
+    are in flight the persistent tcgen05 GEMMs size their grids for `148 - sm_reserve` SMs, so that a NCCL kernel
+    holding a few SMs never pushes statically scheduled tiles into a second wave.
+
+    Semantics = DDP: parameters are broadcast from rank 0 at construction, gradients are averaged over ranks
+    every backward (also with gradient accumulation, like engine_train.py which never uses no_sync())."""
+
+    def __init__(self, model, process_group=None, bucket_mb=200, sm_reserve=0, broadcast=True):
+        from .arena import get_arena
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.backend = dist.get_backend(process_group)
+        self.sm_reserve = int(sm_reserve)
+        arena = get_arena(model)
+        arena.sync = self
+        self.arena = arena
+        self.buckets = self.plan(arena.group_ranges, bucket_mb)
+        self._works = []
+        self._next = 0
+        self._old_budget = None
+        if broadcast and self.world > 1:
+            with torch.no_grad():
+                for p in model.parameters():
+                    dist.broadcast(p.data, 0, group=process_group)
+                for b in model.buffers():
+                    dist.broadcast(b.data, 0, group=process_group)
+
+    @staticmethod
+    def plan(group_ranges, bucket_mb):
+        """[(start, end, last_group_name)]: consecutive stage groups merged until a bucket holds >= bucket_mb MB."""
+        want = int(bucket_mb * (1 << 20) / 4)
+        out, start, last = [], None, None
+        for name, a, b in group_ranges:
+            if start is None:
+                start = a
+            last = (name, b)
+            if b - start >= want:
+                out.append((start, b, name))
+                start = None
+        if start is not None:
+            out.append((start, last[1], last[0]))
+        return out
+
+    # ---- protocol driven by GradArena
+    def begin(self, arena):
+        self._works = []
+        self._next = 0
+        if self.sm_reserve > 0 and arena.slab.is_cuda and self._old_budget is None:
+            from . import ops
+            total = torch.cuda.get_device_properties(arena.slab.device).multi_processor_count
+            self._old_budget = ops.set_sm_budget(total - self.sm_reserve)
+
+    def stage_done(self, arena, name):
+        if self._next < len(self.buckets) and self.buckets[self._next][2] == name:
+            a, b, _ = self.buckets[self._next]
+            self._next += 1
+            if self.world > 1:
+                t = arena.cur[a:b]
+                if self.backend == "nccl":
+                    w = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                    self._works.append((w, None))
+                else:
+                    w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                    self._works.append((w, t))
+
+    def finish(self, arena):
+        if self._next != len(self.buckets):
+            raise RuntimeError("painter_b200.GradSync: backward ended before every gradient bucket was produced")
+        for w, t in self._works:
+            w.wait()
+            if t is not None:
+                t.div_(self.world)
+        self._works = []
+        if self._old_budget is not None:
+            from . import ops
+            ops.set_sm_budget(self._old_budget)
+            self._old_budget = None
+
+
 def average_gradients(params):
     """Reference semantics of DDP's reducer: grad <- mean over ranks (flat bucket, one all-reduce)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

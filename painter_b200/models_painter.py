@@ -12,8 +12,9 @@ from functools import partial
 import torch
 import torch.nn as nn
 
-from . import engine
-from .engine import BlockFn, DecoderFn, EmbedFn, MergeFn
+from . import engine, ops
+from .arena import get_arena
+from .engine import BlockFn, DecoderFn, EmbedFn, MergeFn, StageEnv
 
 
 def trunc_normal_(tensor, mean=0.0, std=1.0):
@@ -70,6 +71,12 @@ class Block(nn.Module):
         return (self.norm1.weight, self.norm1.bias, a.rel_pos_h, a.rel_pos_w, a.qkv.weight, a.qkv.bias,
                 a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias,
                 m.fc2.weight, m.fc2.bias)
+
+    ROLES = ("n1w", "n1b", "rel_h", "rel_w", "qkv_w", "qkv_b", "proj_w", "proj_b", "n2w", "n2b", "fc1_w", "fc1_b",
+             "fc2_w", "fc2_b")
+
+    def roles(self):
+        return dict(zip(self.ROLES, self.params()))
 
 
 class PatchEmbed(nn.Module):
@@ -193,19 +200,43 @@ class Painter(nn.Module):
         return x.reshape(x.shape[0], 3, h * p, w * p)
 
     # ---- the hot path ----
-    def _drop_scales(self, i, Bp, device):
-        """timm DropPath (models_painter.py:199,229-230): per-sample scale floor(keep + U[0,1)) / keep, drawn with
-        torch.rand in the reference's order (attention branch, then MLP branch)."""
-        p = self.blocks[i].drop_prob
-        if not self.training or p == 0.0:
-            return None, None
-        keep = 1.0 - p
+    def _draw_drop_scales(self, B, device):
+        """timm DropPath (models_painter.py:199,229-230) for the whole step: per-sample scales
+        floor(keep + U[0,1)) / keep.  The uniform draws are made with torch.rand in the reference's order, shapes and
+        dtype (attention branch then MLP branch of every block with p > 0; batch 2B up to the early merge; the
+        branch output's dtype, i.e. the autocast dtype) so that a seeded run drops the same branches as the
+        reference; one kernel then turns all of them into scales.  Returns {block: (scale_attn, scale_mlp)}."""
+        if not self.training:
+            return {}
         dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
-        out = []
-        for _ in range(2):
-            r = torch.rand((Bp, 1, 1, 1), dtype=dt, device=device)
-            out.append(((keep + r).floor_().float() / keep).reshape(Bp).contiguous())
-        return out[0], out[1]
+        draws, keeps, slots = [], [], []
+        for i, blk in enumerate(self.blocks):
+            p = blk.drop_prob
+            if p == 0.0:
+                continue
+            Bp = 2 * B if i <= 2 else B
+            for br in range(2):
+                draws.append(torch.rand((Bp, 1, 1, 1), dtype=dt, device=device).reshape(Bp))
+                keeps.append((1.0 - p, Bp))
+                slots.append((i, br, Bp))
+        if not draws:
+            return {}
+        key = (B, str(device), tuple(k for k, _ in keeps))
+        cache = self.__dict__.get("_pk_keep_cache")
+        if cache is None or cache[0] != key:
+            kv = torch.cat([torch.full((n,), k, dtype=torch.float32) for k, n in keeps]).to(device)
+            cache = (key, kv)
+            self.__dict__["_pk_keep_cache"] = cache
+        scales = ops.droppath_scales(torch.cat(draws), cache[1])
+        out, off = {}, 0
+        for i, br, Bp in slots:
+            out.setdefault(i, [None, None])[br] = scales[off:off + Bp]
+            off += Bp
+        return {i: tuple(v) for i, v in out.items()}
+
+    def _drop_scales(self, i, Bp, device):
+        """Per-block view of the step's DropPath scales (tests replace this to replay the reference's CPU draws)."""
+        return self._step_drops.get(i, (None, None))
 
     def _type_emb(self, B, seg_type, device):
         return None
@@ -228,11 +259,19 @@ class Painter(nn.Module):
         mask_u8 = bool_masked_pos.reshape(-1, N).to(torch.uint8).contiguous()
         assert mask_u8.shape[0] in (1, B), "bool_masked_pos must have batch 1 or B"
         pe = self.patch_embed.proj
+        # gradient arena + per-step token (engine.StageEnv): only when this forward can be followed by a backward
+        arena = get_arena(self) if torch.is_grad_enabled() else None
+        token = object()
+        emb_prm = {"w": pe.weight, "b": pe.bias, "mt": self.mask_token, "sx": self.segment_token_x,
+                   "sy": self.segment_token_y, "pe": self.pos_embed}
         z = EmbedFn.apply(imgs, tgts, mask_u8, self._type_emb(B, seg_type, dev), pe.weight, pe.bias, self.mask_token,
-                          self.segment_token_x, self.segment_token_y, self.pos_embed, p, self.pretrain_use_cls_token)
+                          self.segment_token_x, self.segment_token_y, self.pos_embed, p, self.pretrain_use_cls_token,
+                          StageEnv(arena, token, "embed", emb_prm) if arena is not None else None)
         merge_idx = 2
         Bp = 2 * B
         taps = []
+        self._step_drops = self._draw_drop_scales(B, dev)
+        drops = [self._drop_scales(i, 2 * B if i <= merge_idx else B, dev) for i in range(len(self.blocks))]
         for i, blk in enumerate(self.blocks):
             ws = blk.window_size
             if ws > 0 and 112 % ws != 0:
@@ -240,23 +279,35 @@ class Painter(nn.Module):
             ens_g, ens_p = 0, 0
             if merge_between_batch >= 0 and i >= merge_between_batch:
                 ens_g, ens_p = (2, B) if merge_idx >= i else (1, B)
-            da, dm = self._drop_scales(i, Bp, dev)
+            da, dm = drops[i]
             a = blk.attn
             rel_h = engine.resize_rel_table(a.rel_pos_h, ws if ws > 0 else h)
             rel_w = engine.resize_rel_table(a.rel_pos_w, ws if ws > 0 else w)
             prm = blk.params()
+            env = None
+            if arena is not None:
+                # hand-off: block i's dx is consumed only by block i-1's MLP branch (as bf16(DropPath scale * dx))
+                # unless block i-1's output also feeds the early merge or a decoder tap
+                below = None
+                if i > 0 and (i - 1) != merge_idx and (i - 1) not in (5, 11, 17, 23) and ens_g == 0:
+                    below = (self.blocks[i - 1].mlp.fc2.bias, drops[i - 1][1], N)
+                env = StageEnv(arena, token, f"block{i}", blk.roles(), below)
             z = BlockFn.apply(z, da, dm, prm[0], prm[1], rel_h, rel_w, *prm[4:],
-                              (Bp, h, w, self.num_heads, blk.norm1.eps, ens_g, ens_p, ws))
+                              (Bp, h, w, self.num_heads, blk.norm1.eps, ens_g, ens_p, ws), env)
             if i == merge_idx:
                 z = MergeFn.apply(z)
                 Bp = B
             if i in (5, 11, 17, 23):
                 taps.append(z)
         dp = self.decoder_pred
+        dec_prm = {"norm_w": self.norm.weight, "norm_b": self.norm.bias, "dec_w": self.decoder_embed.weight,
+                   "dec_b": self.decoder_embed.bias, "c3_w": dp[0].weight, "c3_b": dp[0].bias, "ln_w": dp[1].weight,
+                   "ln_b": dp[1].bias, "c1_w": dp[3].weight, "c1_b": dp[3].bias}
         loss, patch = DecoderFn.apply(taps[0], taps[1], taps[2], taps[3], self.norm.weight, self.norm.bias,
                                       self.decoder_embed.weight, self.decoder_embed.bias, dp[0].weight, dp[0].bias,
                                       dp[1].weight, dp[1].bias, dp[3].weight, dp[3].bias, tgts, mask_u8, valid,
-                                      (B, h, w, p, self.norm.eps, engine.LOSS_KINDS[self.loss_func], self.seggpt))
+                                      (B, h, w, p, self.norm.eps, engine.LOSS_KINDS[self.loss_func], self.seggpt),
+                                      StageEnv(arena, token, "decoder", dec_prm) if arena is not None else None)
         return loss.reshape(()), patch
 
     def forward(self, imgs, tgts, bool_masked_pos=None, valid=None):

@@ -209,15 +209,19 @@ def assemble_tokens(E, mask_u8, mask_token, seg_x, seg_y, pos, type_emb, B, N, C
     return out
 
 
-def assemble_tokens_bwd(dZ, mask_u8, B, N, C):
+def assemble_tokens_bwd(dZ, mask_u8, B, N, C, token_grads=None):
+    """token_grads: optional (dseg_x, dseg_y, dmask_token) zero-initialised fp32 [C] accumulators (arena views)."""
     dev = dZ.device
     dE = torch.empty((2 * B * N, C), dtype=torch.bfloat16, device=dev)
     dpos = torch.empty((N, C), dtype=torch.float32, device=dev)
-    small = torch.zeros((3, C), dtype=torch.float32, device=dev)
+    if token_grads is None:
+        small = torch.zeros((3, C), dtype=torch.float32, device=dev)
+        token_grads = (small[0], small[1], small[2])
+    sx, sy, mt = token_grads
     check(lib().pk_assemble_tokens_bwd(_ptr(dZ), _ptr(mask_u8), mask_u8.shape[0], _ptr(dE), _ptr(dpos),
-                                       _ptr(small[0]), _ptr(small[1]), _ptr(small[2]), B, N, C, _stream()),
+                                       _ptr(sx), _ptr(sy), _ptr(mt), B, N, C, _stream()),
           "pk_assemble_tokens_bwd")
-    return dE, dpos, small[0], small[1], small[2]
+    return dE, dpos, sx, sy, mt
 
 
 def bicubic_fwd(src, h, w):
@@ -228,9 +232,10 @@ def bicubic_fwd(src, h, w):
     return out
 
 
-def bicubic_bwd(dout, sh, sw):
+def bicubic_bwd(dout, sh, sw, out=None):
+    """out: optional zero-initialised (or running) fp32 [sh, sw, C] accumulator."""
     h, w, C = dout.shape
-    dsrc = torch.zeros((sh, sw, C), dtype=torch.float32, device=dout.device)
+    dsrc = out if out is not None else torch.zeros((sh, sw, C), dtype=torch.float32, device=dout.device)
     check(lib().pk_bicubic_bwd(_ptr(dout), _ptr(dsrc), sh, sw, h, w, C, _stream()), "pk_bicubic_bwd")
     return dsrc
 
@@ -346,11 +351,12 @@ def conv3x3_dgrad_unshuffle(dc1, wd, p):
     return out
 
 
-def conv3x3_wgrad(g_nhwc, dc1):
+def conv3x3_wgrad(g_nhwc, dc1, out=None):
     B, H, W, _ = dc1.shape
     acc = torch.zeros((640, 64), dtype=torch.float32, device=dc1.device)
     check(lib().pk_conv3x3_wgrad(_ptr(g_nhwc), _ptr(dc1), _ptr(acc), B, H, W, _stream()), "pk_conv3x3_wgrad")
-    dw = torch.empty((64, 64, 3, 3), dtype=torch.float32, device=dc1.device)
+    dw = out if out is not None else torch.empty((64, 64, 3, 3), dtype=torch.float32, device=dc1.device)
+    assert dw.is_contiguous() and tuple(dw.shape) == (64, 64, 3, 3)
     check(lib().pk_conv3x3_wgrad_unpack(_ptr(acc), _ptr(dw), _stream()), "pk_conv3x3_wgrad_unpack")
     return dw
 
@@ -373,3 +379,18 @@ def window_unpartition(win, B, H, W, ws, resid=None, rowscale=None):
     check(lib().pk_window_unpartition(_ptr(win), _ptr(resid), _ptr(rowscale), _ptr(out), B, H, W, C, ws, _stream()),
           "pk_window_unpartition")
     return out
+
+
+def droppath_scales(r, keep):
+    """timm DropPath scales for a whole step: r = concatenated torch.rand draws (fp32 / bf16 / fp16, the dtype the
+    reference draws in), keep = per-element keep probability (fp32).  Returns floor(round_dtype(keep + r)) / keep."""
+    code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[r.dtype]
+    assert r.is_contiguous() and keep.is_contiguous() and keep.dtype == torch.float32 and keep.numel() == r.numel()
+    out = torch.empty(r.numel(), dtype=torch.float32, device=r.device)
+    check(lib().pk_droppath_scales(_ptr(r), code, _ptr(keep), _ptr(out), r.numel(), _stream()), "pk_droppath_scales")
+    return out
+
+
+def set_sm_budget(n):
+    """Cap the SM count the persistent kernels size their grids for (0 = all SMs); returns the previous cap."""
+    return int(lib().pk_set_sm_budget(int(n)))

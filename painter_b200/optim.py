@@ -6,6 +6,9 @@ its own `lr` (after `lr_sched.adjust_learning_rate` multiplies by `lr_scale`) an
 decay, bias-corrected first/second moments, fp32 state.  One kernel launch updates every parameter
 (`pk_adamw_step`); unscaling by the AMP loss scale and gradient clipping ride along as a device-side multiplier,
 the way `util/misc.py:252-278` sequences unscale -> clip -> step, without extra passes over the gradients.
+The same pass refreshes the bf16 operand copies of the GEMM weights / rel-pos tables (engine.bf16_weight) and, when
+the gradients live in the module's flat arena (painter_b200/arena.py), clears them for the next backward - so a
+training step launches no cast and no fill kernels.
 `global_grad_norm` is `misc.get_grad_norm_` / `clip_grad_norm_`'s 2-norm in one launch (`pk_grad_sumsq`).
 """
 import ctypes
@@ -15,12 +18,13 @@ import torch
 
 from ._lib import check, lib
 
-_REC = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("lr", "<f4"), ("wd", "<f4")])
-assert _REC.itemsize == 48
+_REC = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("w16", "<u8"), ("n", "<i8"),
+                 ("lr", "<f4"), ("wd", "<f4")])
+assert _REC.itemsize == 56
 
 
 def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
 def _stream():
@@ -46,12 +50,20 @@ def _chunk_table(numels, device):
     return tab
 
 
-def _tensor_table(entries, device):
-    """entries: list of (p, g, m, v, lr, wd) fp32 contiguous CUDA tensors (m / v may be None) -> device uint8 table."""
+def _tensor_table(entries, device, cache=None):
+    """entries: list of (p, g, m, v, w16, lr, wd) (m / v / w16 may be None) -> device uint8 table of PkOptTensor.
+    `cache` (a dict) keeps the device copy while the host records are unchanged (static pointers, lr and wd)."""
     rec = np.zeros(len(entries), dtype=_REC)
-    for i, (p, g, m, v, lr, wd) in enumerate(entries):
+    for i, (p, g, m, v, w16, lr, wd) in enumerate(entries):
         rec[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr() if m is not None else 0,
-                  v.data_ptr() if v is not None else 0, p.numel(), lr, wd)
+                  v.data_ptr() if v is not None else 0, w16.data_ptr() if w16 is not None else 0, p.numel(), lr, wd)
+    if cache is not None:
+        raw = rec.tobytes()
+        if cache.get("raw") == raw and cache["dev"].device == torch.device(device):
+            return cache["dev"]
+        cache["raw"] = raw
+        cache["dev"] = torch.from_numpy(rec.view(np.uint8)).to(device)
+        return cache["dev"]
     return torch.from_numpy(rec.view(np.uint8)).to(device)
 
 
@@ -62,13 +74,18 @@ def _check_fp32(t, what):
 
 def global_grad_norm(parameters):
     """2-norm of all gradients as a 0-dim device tensor (no host sync): `misc.get_grad_norm_(params, 2.0)`."""
+    parameters = list(parameters)
     grads = [p.grad for p in parameters if p.grad is not None]
     if not grads:
         return torch.zeros((), device="cuda")
     dev = grads[0].device
+    ref = getattr(parameters[0], "_pk_arena", None)
+    arena = ref() if ref is not None else None
+    if arena is not None and len(grads) == len(arena.params) and arena.grads_in_arena():
+        grads = [arena.slab]      # every gradient lives in the flat arena (padding is zero): one contiguous pass
     for g in grads:
         _check_fp32(g, "gradient")
-    table = _tensor_table([(g, g, None, None, 0.0, 0.0) for g in grads], dev)
+    table = _tensor_table([(g, g, None, None, None, 0.0, 0.0) for g in grads], dev)
     chunks = _chunk_table([g.numel() for g in grads], dev)
     out = torch.zeros(1, dtype=torch.float32, device=dev)
     check(lib().pk_grad_sumsq(_ptr(table), _ptr(chunks), chunks.shape[0], _ptr(out), _stream()), "pk_grad_sumsq")
@@ -76,55 +93,89 @@ def global_grad_norm(parameters):
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, arena=None):
+        """arena: the module's painter_b200.arena.GradArena (optional; found through the parameters otherwise)."""
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
+        self._arena = arena
+        self._tables = {}
+
+    def _find_arena(self, params):
+        if self._arena is not None:
+            return self._arena
+        for p in params:
+            ref = getattr(p, "_pk_arena", None)
+            if ref is not None:
+                return ref()
+        return None
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=None, grad_scale_cap=0.0):
+    def step(self, closure=None, grad_scale=None, grad_scale_cap=0.0, found_inf=None):
         """grad_scale: optional 1-element fp32 device tensor every gradient is multiplied by (1 / loss scale, or the
-        clip coefficient max_norm / (norm + 1e-6)); grad_scale_cap > 0 clamps it from above (clip: cap = 1)."""
+        clip coefficient max_norm / (norm + 1e-6)); grad_scale_cap > 0 clamps it from above (clip: cap = 1).
+        found_inf: optional 1-element fp32 device tensor; non-zero turns the step into a no-op (GradScaler.step)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         # groups may differ in betas / eps / step count (they do not in the reference): one launch per such class
         classes = {}
+        stepped = []
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
                 if p.grad is None:
                     continue
                 st = self.state[p]
-                if not st:
+                if "exp_avg" not in st:
                     _check_fp32(p, "parameter")
                     st["step"] = 0
-                elif torch.is_tensor(st["step"]):     # state loaded from a torch.optim.AdamW checkpoint (misc.load_model)
-                    st["step"] = int(st["step"].item())
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                elif torch.is_tensor(st["step"]):   # state loaded from a torch.optim.AdamW checkpoint (misc.load_model)
+                    st["step"] = int(st["step"].item())
                 st["step"] += 1
                 g = p.grad
                 if not g.is_contiguous():
                     g = g.contiguous()
                 _check_fp32(g, "gradient")
+                ent = getattr(p, "_pk_bf16", None)   # bf16 operand copy kept by engine.bf16_weight / bf16_table
+                w16 = ent[2] if ent is not None and ent[1] == p.data_ptr() and ent[2].device == p.device else None
                 key = (b1, b2, group["eps"], st["step"])
-                classes.setdefault(key, []).append((p, g, st["exp_avg"], st["exp_avg_sq"], group["lr"],
+                classes.setdefault(key, []).append((p, g, st["exp_avg"], st["exp_avg_sq"], w16, group["lr"],
                                                     group["weight_decay"]))
-        for (b1, b2, eps, step), entries in classes.items():
+                stepped.append(p)
+        if not stepped:
+            return loss
+        arena = self._find_arena(stepped)
+        zero = 0
+        if arena is not None and found_inf is None:
+            # every slot of the arena is consumed by this step -> leave it zeroed for the next backward
+            ids = {id(p) for p in stepped}
+            if all(id(p) in ids for p in arena.params) and arena.grads_in_arena():
+                zero = 1
+        for ci, ((b1, b2, eps, step), entries) in enumerate(classes.items()):
             dev = entries[0][0].device
             chunks = _chunk_table([e[0].numel() for e in entries], dev)
-            table = _tensor_table(entries, dev)
+            table = _tensor_table(entries, dev, self._tables.setdefault(ci, {}))
             gs = None
             if grad_scale is not None:
                 gs = grad_scale.reshape(-1)[:1]
                 _check_fp32(gs, "grad_scale")
+            fi = None
+            if found_inf is not None:
+                fi = found_inf.reshape(-1)[:1]
+                _check_fp32(fi, "found_inf")
             check(lib().pk_adamw_step(_ptr(table), _ptr(chunks), chunks.shape[0], ctypes.c_double(b1),
-                                      ctypes.c_double(b2), ctypes.c_double(eps), step,
-                                      _ptr(gs) if gs is not None else None, ctypes.c_float(grad_scale_cap),
-                                      _stream()), "pk_adamw_step")
-            # the kernel wrote through raw pointers: tell autograd (and engine.bf16_weight's (version, storage) cache
-            # key) that the parameters changed, as an in-place torch op would
+                                      ctypes.c_double(b2), ctypes.c_double(eps), step, _ptr(gs),
+                                      ctypes.c_float(grad_scale_cap), zero, _ptr(fi), _stream()), "pk_adamw_step")
+            # the kernel wrote through raw pointers: tell autograd (and the (version, storage) key of the bf16 operand
+            # cache, whose copy the kernel has just refreshed) that the parameters changed, as an in-place op would
             for e in entries:
-                torch.autograd.graph.increment_version(e[0])
+                p = e[0]
+                torch.autograd.graph.increment_version(p)
+                if e[4] is not None:
+                    p._pk_bf16 = (p._version, p.data_ptr(), e[4])
+        if zero:
+            arena.mark_clean()
         return loss

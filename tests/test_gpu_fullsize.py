@@ -165,8 +165,18 @@ def test_seggpt_vitl_run_one_image_unmodified_engine():
         ref.seg_type = model.seg_type = seg
         with strict_fp32():
             out_f = se.run_one_image(img, tgt, ref, dev)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out_b = se.run_one_image(img, tgt, ref, dev)
+        # the reference's own bf16 noise: run_one_image cannot run under autocast (numpy cannot take its bf16 result),
+        # so the same call sequence (seggpt_engine.py:29-52) is restated around the reference MODULE for this one
+        # measurement
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            bm = torch.zeros(1, ref.patch_embed.num_patches)
+            bm[:, ref.patch_embed.num_patches // 2:] = 1
+            xt, tt = torch.tensor(img).permute(0, 3, 1, 2), torch.tensor(tgt).permute(0, 3, 1, 2)
+            sgt = torch.ones(P, 1) if seg == "instance" else torch.zeros(P, 1)
+            _, yb, _ = ref(xt.float().to(dev), tt.float().to(dev), bm.to(dev), torch.ones_like(tt).float().to(dev),
+                           sgt.to(dev), 0 if P > 1 else -1)
+        yb = ref.unpatchify(yb.float()).permute(0, 2, 3, 1).cpu()
+        out_b = torch.clip((yb[0, yb.shape[1] // 2:] * se.imagenet_std + se.imagenet_mean) * 255, 0, 255)
         out_o = se.run_one_image(img, tgt, model, dev)
         assert tuple(out_o.shape) == tuple(out_f.shape) == (448, 448, 3) and out_o.dtype == out_f.dtype
         eo, eb = rms_rel(out_o, out_f), rms_rel(out_b, out_f)

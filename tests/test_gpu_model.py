@@ -238,3 +238,74 @@ def test_fused_adamw_trains_the_gemm_weights():
         assert not torch.equal(before, w.detach()), "parameter did not move"
         assert torch.equal(engine.bf16_weight(w), w.detach().bfloat16()), "stale bf16 weight cache after the step"
     assert losses[-1] < losses[0], losses
+
+
+def test_gradient_arena_views_accumulation_and_fused_step():
+    """painter_b200/arena.py: p.grad is a view of the flat arena after a backward; a second backward without
+    zero_grad accumulates (scratch slab) to exactly twice the gradient; FusedAdamW consumes and clears the arena and
+    takes the same step as torch.optim.AdamW."""
+    from painter_b200.arena import get_arena
+    from painter_b200.optim import FusedAdamW, global_grad_norm
+    cfg = po.PainterConfig(img_size=(128, 64), embed_dim=128, num_heads=2, decoder_embed_dim=64)
+    model, _ = build_model(cfg, 0)
+    twin, _ = build_model(cfg, 0)
+    model.eval()
+    twin.eval()
+    imgs, tgts, mask, valid = _to("cuda", *synth_inputs(cfg, 2, 3, valid_kind="mixed"))
+    loss, _, _ = model(imgs, tgts, mask, valid)
+    loss.backward()
+    arena = get_arena(model)
+    assert arena.grads_in_arena()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters()}
+    n1 = global_grad_norm(model.parameters()).item()
+    ref_norm = torch.sqrt(sum(g.double().pow(2).sum() for g in g1.values())).item()
+    assert abs(n1 - ref_norm) <= 1e-5 * ref_norm
+    loss, _, _ = model(imgs, tgts, mask, valid)
+    loss.backward()                                         # accumulation: p.grad is live
+    for n, p in model.named_parameters():
+        assert rel_rms(p.grad, 2 * g1[n]) < 1e-5, n
+    assert arena.grads_in_arena()
+    # one optimizer step from the single-backward gradient, against torch.optim.AdamW on an identical twin
+    for p in model.parameters():
+        p.grad = None
+    loss, _, _ = model(imgs, tgts, mask, valid)
+    loss.backward()
+    lt, _, _ = twin(imgs, tgts, mask, valid)
+    lt.backward()
+    opt = FusedAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05)
+    topt = torch.optim.AdamW(twin.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05)
+    opt.step()
+    topt.step()
+    torch.cuda.synchronize()
+    assert arena.clean and float(arena.slab.abs().max()) == 0.0, "the fused step must leave the arena zeroed"
+    worst = max(((p - q).abs().max() / q.abs().max().clamp_min(1e-12)).item()
+                for p, q in zip(model.parameters(), twin.parameters()))
+    # Adam's first step is lr * sign(g) wherever |g| >> eps: a sign flip of a ~0 gradient moves a weight by 2 lr
+    assert worst < 5e-2, worst
+    frac_same = sum(((p - q).abs() <= 1e-6 + 1e-4 * q.abs()).sum().item() for p, q in
+                    zip(model.parameters(), twin.parameters())) / sum(p.numel() for p in model.parameters())
+    assert frac_same > 0.98, frac_same
+    opt.zero_grad(set_to_none=True)
+    loss2, _, _ = model(imgs, tgts, mask, valid)            # next step runs on the kernel-refreshed bf16 operands
+    loss2.backward()
+    assert arena.grads_in_arena() and torch.isfinite(loss2)
+
+
+def test_nccl_world2_gradsync_equals_mean_of_rank_gradients(tmp_path):
+    """GradSync over NCCL on the CUDA module (needs 2 GPUs): the synchronised gradient of every parameter equals the
+    mean of the two ranks' local gradients."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "nccl.json")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611",
+                        os.path.join(root, "scripts", "nccl_gradsync_check.py"), out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    import json
+    res = json.load(open(out))
+    assert res["max_rel_err"] < 1e-5, res

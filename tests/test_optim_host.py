@@ -10,12 +10,12 @@ from painter_b200 import _lib, optim
 
 class PkOptTensor(ctypes.Structure):   # as declared in include/painter_b200.h
     _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
-                ("n", ctypes.c_longlong), ("lr", ctypes.c_float), ("wd", ctypes.c_float)]
+                ("w16", ctypes.c_void_p), ("n", ctypes.c_longlong), ("lr", ctypes.c_float), ("wd", ctypes.c_float)]
 
 
 def test_record_layout_matches_the_c_struct():
-    assert optim._REC.itemsize == ctypes.sizeof(PkOptTensor) == 48
-    for name in ("p", "g", "m", "v", "n", "lr", "wd"):
+    assert optim._REC.itemsize == ctypes.sizeof(PkOptTensor) == 56
+    for name in ("p", "g", "m", "v", "w16", "n", "lr", "wd"):
         assert optim._REC.fields[name][1] == getattr(PkOptTensor, name).offset
 
 
@@ -35,7 +35,13 @@ def test_chunk_table_tiles_every_tensor_once():
 def test_tensor_table_carries_pointers_sizes_and_group_hyperparameters():
     p, g = torch.zeros(10), torch.ones(10)
     m, v = torch.zeros(10), torch.zeros(10)
-    raw = optim._tensor_table([(p, g, m, v, 3e-3, 0.05)], torch.device("cpu")).numpy().tobytes()
+    w16 = torch.zeros(10, dtype=torch.bfloat16)
+    cache = {}
+    tab = optim._tensor_table([(p, g, m, v, w16, 3e-3, 0.05)], torch.device("cpu"), cache)
+    assert optim._tensor_table([(p, g, m, v, w16, 3e-3, 0.05)], torch.device("cpu"), cache) is tab   # cached
+    assert optim._tensor_table([(p, g, m, v, w16, 4e-3, 0.05)], torch.device("cpu"), cache) is not tab  # lr changed
+    raw = tab.numpy().tobytes()
     rec = PkOptTensor.from_buffer_copy(raw)
     assert (rec.p, rec.g, rec.m, rec.v, rec.n) == (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 10)
+    assert rec.w16 == w16.data_ptr()
     assert abs(rec.lr - 3e-3) < 1e-9 and abs(rec.wd - 0.05) < 1e-8

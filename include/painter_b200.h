@@ -211,6 +211,27 @@ int pk_droppath_scales(const void* r, int dtype_code, const float* keep, float* 
  * so that statically partitioned tiles never run as a second wave (multi-GPU backward).  Returns the old value. */
 int pk_set_sm_budget(int n);
 
+/* ------------------------------------------------------------------------------------------------
+ * Inference pre/post-processing on the device.  Replaces the numpy / torch-CPU arithmetic around the
+ * forward in SegGPT/SegGPT_inference/seggpt_engine.py:26-53 (run_one_image), :56-103 (inference_image), :106-181
+ * (inference_video) and Painter/eval/ade20k_semantic/painter_inference_segm.py:67-93 (run_one_image).
+ * dtype codes of image sources: 0 = uint8 (divided by 255.), 1 = fp32 in [0,1], 2 = fp64 in [0,1].
+ *  pk_stitch_normalize  canvas[p,c,y,x] fp32 NCHW [P,3,2S,S] = ((top|bottom)[p][y%S,x,c] - mean_c) / std_c in fp64
+ *                       (:75-91 stitch + ImageNet normalisation, :29-34 nhwc->nchw .float()); host arrays of P device
+ *                       pointers
+ *  pk_nhwc_to_nchw_f32  torch.einsum('nhwc->nchw', x).float() of an already normalised fp64/fp32 batch (:29-34)
+ *  pk_seg_postprocess   out fp64 [h*p/2, w*p, 3] = clip((unpatchify(patch)[0, bottom half] * std + mean) * 255, 0, 255)
+ *                       (:48-52); bin (nullable) fp32 [h*p/2, w*p] = mean_c(out) > 128 (:164-169, video cache)
+ *  pk_nearest_blend     dst uint8 [OH,OW,3] = uint8(image * (0.6 * nearest(seg) / 255 + 0.4)) (:93-102)
+ *  pk_bilinear_u8       dst uint8 [OH,OW,3] = uint8(int(bilinear(seg))) (painter_inference_segm.py:89-92)        */
+int pk_stitch_normalize(const void* const* top, const int* top_dtype, const void* const* bottom,
+                        const int* bottom_dtype, float* out, int P, int S, void* stream);
+int pk_nhwc_to_nchw_f32(const void* in, int in_is_f64, float* out, int n, int H, int W, void* stream);
+int pk_seg_postprocess(const float* patch, double* out, float* bin_or_null, int h, int w, int p, void* stream);
+int pk_nearest_blend(const double* seg, int SH, int SW, const uint8_t* image, uint8_t* dst, int OH, int OW,
+                     void* stream);
+int pk_bilinear_u8(const double* seg, int SH, int SW, uint8_t* dst, int OH, int OW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

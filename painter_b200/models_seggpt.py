@@ -22,12 +22,12 @@ class SegGPT(Painter):
         torch.nn.init.normal_(self.type_token_ins, std=.02)
 
     def _type_emb(self, B, seg_type, device):
-        # models_seggpt.py:415-417 — tiny [B, C] parameter gather, done with torch indexing on the host side
+        # models_seggpt.py:415-417 - tiny [B, C] parameter select (mask arithmetic instead of boolean indexing: no
+        # host synchronisation, so the forward stays CUDA-graph capturable)
         C = self.embed_dim
-        te = torch.zeros(B, C, device=device)
-        st = seg_type.reshape(B).to(device)
-        te[st == 0] = self.type_token_cls.reshape(1, C).to(te.dtype)
-        te[st == 1] = self.type_token_ins.reshape(1, C).to(te.dtype)
+        st = seg_type.reshape(B, 1).to(device=device, dtype=torch.float32)
+        te = (st == 0).to(torch.float32) * self.type_token_cls.reshape(1, C).float() + \
+             (st == 1).to(torch.float32) * self.type_token_ins.reshape(1, C).float()
         return te.detach().contiguous()
 
     def forward(self, imgs, tgts, bool_masked_pos=None, valid=None, seg_type=None, merge_between_batch=-1):

@@ -35,22 +35,41 @@ def _peaks():
         return 1400.0, "fallback (B200_PROFILING.md sustained bf16)"
 
 
-def _masks(B, seed):
-    """BEiT block masks drawn by the reference MaskingGenerator (fixture made by oracle/make_golden.py)."""
+def _masks(B, seed, up=1):
+    """BEiT block masks drawn by the reference MaskingGenerator (fixture made by oracle/make_golden.py); up = 2
+    repeats every mask cell 2x2 for the 112x56 token grid of the 1792x896 workload."""
     import numpy as np
     import torch
     packed = torch.load(os.path.join(ROOT, "tests", "golden", "beit_masks_56x28.pt"), weights_only=False).numpy()
     m = np.unpackbits(packed, axis=-1)[..., :28]
     idx = [(seed * 7 + i) % m.shape[0] for i in range(B)]
-    return torch.from_numpy(m[idx].astype("int32"))
+    t = torch.from_numpy(m[idx].astype("int32"))
+    if up > 1:
+        t = t.repeat_interleave(up, 1).repeat_interleave(up, 2)
+    return t
 
 
-def _batch(B, seed):
+def _batch(B, seed, Hh=None, Ww=None):
     import torch
+    Hh, Ww = Hh or H, Ww or W
     g = torch.Generator().manual_seed(1234 + seed)
-    imgs = torch.randn(B, 3, H, W, generator=g)
-    tgts = torch.randn(B, 3, H, W, generator=g)
-    return imgs, tgts, _masks(B, seed), torch.ones(B, 3, H, W)
+    imgs = torch.randn(B, 3, Hh, Ww, generator=g)
+    tgts = torch.randn(B, 3, Hh, Ww, generator=g)
+    return imgs, tgts, _masks(B, seed, Hh // H), torch.ones(B, 3, Hh, Ww)
+
+
+# BASELINE.json configs the bench can run: [1]/[3] "train" (the headline), [4] "long", [2] "seggpt" (run_seggpt)
+WORKLOADS = {
+    "train": dict(H=896, W=448, batch=8, flops=4769.23e9, tokens=1568,
+                  name="ViT-L 896x448 bf16 MIM train step (fwd+bwd+AdamW), batch 8 per GPU "
+                       "(BASELINE.json configs[1]; configs[3] at 8 GPUs)",
+                  metric="images/sec ViT-L 896x448 MIM train step"),
+    "long": dict(H=1792, W=896, batch=2, flops=28952.86e9, tokens=6272,
+                 name="ViT-L 1792x896 long-sequence bf16 MIM train step (fwd+bwd+AdamW), 6272 tokens, batch 2 per GPU "
+                      "(BASELINE.json configs[4])",
+                 metric="images/sec ViT-L 1792x896 MIM train step"),
+}
+FLOPS_SEGGPT_FWD = 1589.74e9        # SURVEY.md section 8(d): SegGPT 1-prompt inference = one 896x448 forward
 
 
 class ClockSampler:
@@ -172,6 +191,172 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _seggpt_inputs(P=1, seed=0):
+    """What seggpt_engine.inference_image hands to run_one_image: [P, 896, 448, 3] float64 ImageNet-normalised canvases
+    (prompt over query; prompt target over a copy of itself)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    img = (rng.rand(P, 896, 448, 3) - mean) / std
+    half = (rng.rand(P, 448, 448, 3) > 0.5).astype(np.float64)
+    tgt = (np.concatenate([half, half], axis=1) - mean) / std
+    return img, tgt
+
+
+def run_seggpt_reference(args):
+    """--impl reference --workload seggpt: the unmodified reference SegGPT module driven by the unmodified
+    seggpt_engine.run_one_image on the host cores (torch-CPU eager fp32)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from oracle import painter_oracle as po
+    from oracle import ref_loader
+    from oracle.synth import synth_state_dict
+    threads = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(threads)
+    se = ref_loader.seggpt_engine()
+    model = ref_loader.models_seggpt().seggpt_vit_large_patch16_input896x448()
+    model.load_state_dict(synth_state_dict(po.PainterConfig(seggpt=True), 0), strict=True)
+    model.eval()
+    model.seg_type = "instance"
+    img, tgt = _seggpt_inputs()
+    times = []
+    for _ in range(1 + min(args.steps, 5)):
+        t0 = time.perf_counter()
+        se.run_one_image(img, tgt, model, torch.device("cpu"))
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times[1:]) / len(times[1:])
+    val = 1e3 / ms
+    print(json.dumps({
+        "impl": "reference", "metric": "images/sec SegGPT ViT-L in-context inference (1 prompt + 1 target 448x448)",
+        "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "SegGPT ViT-L run_one_image, 1 prompt pair + 1 target (BASELINE.json "
+                                                    "configs[2]) on host cores", "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "reference",
+                         "sample": f"{len(times) - 1} x seggpt_engine.run_one_image (unmodified reference), torch-CPU "
+                                   "eager fp32, after 1 warm-up"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def run_seggpt(args):
+    """BASELINE.json configs[2]: SegGPT ViT-L in-context segmentation, 1 prompt pair + 1 target 448x448, 1 GPU.
+    step = one forward of the stitched 896x448 canvases.  `value`: canvases resident in HBM, the forward replayed as
+    ONE CUDA graph (painter_b200/graphs.py).  `e2e`: painter_b200.seggpt_engine.run_one_image - the reference entry
+    point's signature - from host numpy arrays to the de-normalised result back on the host.  N > 1: independent
+    replicas (inference shards by image; no collective), every rank runs the same loop."""
+    if args.impl == "reference":
+        return run_seggpt_reference(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from painter_b200 import _lib, dist_utils, models_seggpt, seggpt_engine
+    from painter_b200.graphs import GraphedForward
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = models_seggpt.seggpt_vit_large_patch16_input896x448().to(dev).eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "rel_pos" in n:
+                p.normal_(std=0.02)
+    model.seg_type = "instance"
+    img, tgt = _seggpt_inputs()
+    steps, W_steps = max(args.steps, 1), max(args.warmup, 3)
+    x = torch.from_numpy(img).permute(0, 3, 1, 2).float().contiguous().to(dev)
+    t = torch.from_numpy(tgt).permute(0, 3, 1, 2).float().contiguous().to(dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        sync()
+        return a.elapsed_time(b) / n
+
+    # eager (one launch per kernel) for comparison, then the graph replay
+    mask = seggpt_engine._half_mask(model, dev)
+    valid = torch.ones_like(t)
+    seg = torch.ones(1, 1, device=dev)
+
+    def eager():
+        with torch.no_grad():
+            model(x, t, mask, valid, seg, -1)
+
+    for _ in range(W_steps):
+        eager()
+    n0 = _lib.launch_count()
+    ms_eager = timed(eager, steps)
+    launches = (_lib.launch_count() - n0) // steps
+    gf = GraphedForward(model)
+    for _ in range(W_steps):
+        gf(x, t, mask, valid, seg, -1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_graph = timed(lambda: gf(x, t, mask, valid, seg, -1), steps * 5) 
+    for _ in range(W_steps):
+        seggpt_engine.run_one_image(img, tgt, model, dev)
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = seggpt_engine.run_one_image(img, tgt, model, dev)
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / steps
+    clk = clocks.stop() if rank == 0 else None
+    ms_graph, ms_e2e, ms_eager = dist_utils.max_over_ranks([ms_graph, ms_e2e, ms_eager], device=dev)
+    if rank == 0:
+        peak, peak_src = _peaks()
+        achieved = FLOPS_SEGGPT_FWD / (ms_graph / 1e3) / 1e12
+        line = {
+            "metric": "images/sec SegGPT ViT-L in-context inference (1 prompt + 1 target 448x448)",
+            "value": world * 1e3 / ms_graph, "unit": "images/s", "n_gpus": world, "steps": steps * 5, "warmup": W_steps,
+            "ms_per_step": ms_graph, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "SegGPT ViT-L in-context segmentation inference, 1 prompt pair + 1 target 448x448 "
+                                   "(BASELINE.json configs[2]); replicas only when N > 1",
+                       "parallelism": "single" if world == 1 else f"{world} replicas", "tokens_per_image": 1568,
+                       "forward": "one CUDA-graph replay of the whole forward", "kernels_per_forward": int(launches),
+                       "eager_ms_per_step": ms_eager,
+                       "l2": "weights (0.74 GB bf16) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": world * 1e3 / ms_e2e, "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(img.nbytes + tgt.nbytes), "d2h_bytes_per_step": int(out.numel() * 8),
+                    "call": "painter_b200.seggpt_engine.run_one_image(img, tgt, model, device): numpy float64 canvases in, "
+                            "de-normalised [448,448,3] float64 result on the host out (wall clock incl. both copies)"},
+            "gpu_launches": int(launches) * steps * 5,
+            "roofline": {"bound": "tensor", "kernel": "whole forward (tcgen05 GEMMs + fused attention), one graph replay",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_per_launch": FLOPS_SEGGPT_FWD, "traffic": None},
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import painter_oracle as po  # noqa: F401  (checker / baseline leg only)
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "seggpt",
+                                "--steps", "2"], capture_output=True, text=True)
+            try:
+                line["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception:
+                line["cpu_baseline"] = {"error": (r.stderr or r.stdout)[-300:]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
@@ -188,12 +373,19 @@ def main():
                          "from backward; default) or stock DistributedDataParallel")
     ap.add_argument("--sm-reserve", type=int, default=8,
                     help="N > 1, --dp own: SMs left to NCCL while gradient buckets are in flight")
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--workload", default="train", choices=["train", "long", "seggpt"],
+                    help="train = BASELINE configs[1]/[3] (headline), long = configs[4], seggpt = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="diagnostic only; the reported step includes AdamW")
     args = ap.parse_args()
+    if args.workload == "seggpt":
+        return run_seggpt(args)
     if args.impl == "reference":
         return run_reference(args)
+    wl = WORKLOADS[args.workload]
+    if args.batch <= 0:
+        args.batch = wl["batch"]
 
     import torch
     import torch.distributed as dist
@@ -212,7 +404,15 @@ def main():
     B = args.batch
 
     torch.manual_seed(0)
-    model = models_painter.painter_vit_large_patch16_input896x448_win_dec64_8glb_sl1().to(dev)
+    if args.workload == "long":
+        from functools import partial
+        model = models_painter.Painter(
+            img_size=(1792, 896), patch_size=16, embed_dim=1024, depth=24, num_heads=16, drop_path_rate=0.1,
+            window_size=14, qkv_bias=True, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+            window_block_indexes=(), residual_block_indexes=[], use_rel_pos=True, out_feature="last_feat",
+            decoder_embed_dim=64, loss_func="smoothl1").to(dev)
+    else:
+        model = models_painter.painter_vit_large_patch16_input896x448_win_dec64_8glb_sl1().to(dev)
     with torch.no_grad():
         for n, p in model.named_parameters():
             if "rel_pos" in n:
@@ -236,7 +436,7 @@ def main():
         opt = torch.optim.AdamW(groups, lr=1e-4, betas=(0.9, 0.999), fused=True)
     adjust_learning_rate(opt, 1.0, 1e-4, 0.0, 1, 15)
 
-    host = [t.pin_memory() for t in _batch(B, dist_utils.rank_seed(0, rank) % 9973)]
+    host = [t.pin_memory() for t in _batch(B, dist_utils.rank_seed(0, rank) % 9973, wl["H"], wl["W"])]
     resident = [t.to(dev) for t in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
@@ -370,13 +570,12 @@ def main():
         except (OSError, KeyError, ValueError):
             pass
         line = {
-            "metric": "images/sec ViT-L 896x448 MIM train step", "value": value, "unit": "images/s",
+            "metric": wl["metric"], "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": W_steps, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ViT-L 896x448 bf16 MIM train step (fwd+bwd+AdamW), batch 8 per GPU "
-                                   "(BASELINE.json configs[1]; configs[3] at 8 GPUs)",
+            "config": {"workload": wl["name"],
                        "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single",
-                       "tokens_per_image": 1568,
+                       "tokens_per_image": wl["tokens"],
                        "optimizer": "none" if args.no_optimizer else (
                            "AdamW over lr_decay.param_groups_lrd groups (layer_decay 0.8, wd 0.05): " +
                            ("painter_b200.optim.FusedAdamW" if args.optimizer == "pk" else "torch fused AdamW")),
@@ -397,10 +596,10 @@ def main():
                          "frac": achieved / peak if peak else None, "peak_source": peak_src,
                          "launches": len(gemm_log), "share_of_step": gms / ms_total, "traffic": traffic,
                          "algorithmic_per_launch": flops / max(len(gemm_log), 1),
-                         "step_mfu": value / world * FLOPS_PER_IMAGE_TRAIN / 1e12 / peak},
+                         "step_mfu": value / world * wl["flops"] / 1e12 / peak},
             "clocks": clk, "loss": last_loss,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "train":
             threads = min(os.cpu_count() or 1, 32)
             ts, kind = cpu_reference_step_time(threads, reps=2)
             line["cpu_baseline"] = {"value": 1.0 / ts[-1], "unit": "images/s", "cores": threads, "kind": kind,

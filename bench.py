@@ -297,26 +297,40 @@ def run_seggpt(args):
         with torch.no_grad():
             model(x, t, mask, valid, seg, -1)
 
-    for _ in range(W_steps):
-        eager()
-    n0 = _lib.launch_count()
-    ms_eager = timed(eager, steps)
-    launches = (_lib.launch_count() - n0) // steps
-    gf = GraphedForward(model)
-    for _ in range(W_steps):
-        gf(x, t, mask, valid, seg, -1)
+    def measure(precision, n_graph):
+        model.precision = precision
+        for _ in range(W_steps):
+            eager()
+        n0 = _lib.launch_count()
+        ms_eager = timed(eager, steps)
+        launches = (_lib.launch_count() - n0) // steps
+        gf = GraphedForward(model)
+        for _ in range(W_steps):
+            gf(x, t, mask, valid, seg, -1)
+        ms_graph = timed(lambda: gf(x, t, mask, valid, seg, -1), n_graph)
+        for _ in range(W_steps):
+            seggpt_engine.run_one_image(img, tgt, model, dev)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = seggpt_engine.run_one_image(img, tgt, model, dev)
+        torch.cuda.synchronize()
+        ms_e2e = 1e3 * (time.perf_counter() - t0) / steps
+        return ms_eager, ms_graph, ms_e2e, launches, out
+
+    # fp32-accurate mode first (reported as an extra block), then the headline bf16 mode under the clock sampler
+    acc = None
+    if args.precision in ("both", "fp32"):
+        a_eager, a_graph, a_e2e, a_launches, _ = measure("fp32", max(steps, 3))
+        acc = {"ms_per_step": a_graph, "value": world * 1e3 / a_graph, "eager_ms_per_step": a_eager,
+               "e2e_ms_per_step": a_e2e, "e2e_value": world * 1e3 / a_e2e, "kernels_per_forward": int(a_launches),
+               "note": "model.precision = 'fp32': split-bf16 (3 terms, 6 products) tensor-core GEMMs, fp32 softmax / "
+                       "LayerNorm / exact-erf GELU; what precision='auto' selects for the reference's fp32 inference "
+                       "calls (parity <= 1e-5, tests/test_gpu_accurate.py)"}
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms_graph = timed(lambda: gf(x, t, mask, valid, seg, -1), steps * 5) 
-    for _ in range(W_steps):
-        seggpt_engine.run_one_image(img, tgt, model, dev)
-    sync()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        out = seggpt_engine.run_one_image(img, tgt, model, dev)
-    torch.cuda.synchronize()
-    ms_e2e = 1e3 * (time.perf_counter() - t0) / steps
+    ms_eager, ms_graph, ms_e2e, launches, out = measure("bf16", steps * 5)
     clk = clocks.stop() if rank == 0 else None
     ms_graph, ms_e2e, ms_eager = dist_utils.max_over_ranks([ms_graph, ms_e2e, ms_eager], device=dev)
     if rank == 0:
@@ -343,6 +357,8 @@ def run_seggpt(args):
                          "peak_source": peak_src, "algorithmic_per_launch": FLOPS_SEGGPT_FWD, "traffic": None},
             "clocks": clk,
         }
+        if acc is not None:
+            line["fp32_accurate"] = acc
         if not args.no_cpu_baseline and world == 1:
             from oracle import painter_oracle as po  # noqa: F401  (checker / baseline leg only)
             import subprocess
@@ -374,6 +390,8 @@ def main():
     ap.add_argument("--sm-reserve", type=int, default=8,
                     help="N > 1, --dp own: SMs left to NCCL while gradient buckets are in flight")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--precision", default="both", choices=["bf16", "fp32", "both"],
+                    help="seggpt workload: also time the fp32-accurate mode (reported under 'fp32_accurate')")
     ap.add_argument("--workload", default="train", choices=["train", "long", "seggpt"],
                     help="train = BASELINE configs[1]/[3] (headline), long = configs[4], seggpt = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -498,20 +516,23 @@ def main():
     record["on"] = False
     ms_total = e0.elapsed_time(e1)
     # ---------------- timed region 2: end to end through the public API, the reference loop's way ----------------
-    # Every step: the batch comes from pinned host memory (painter_b200.data_utils.DevicePrefetcher issues the same
-    # .to(device, non_blocking=True) copies as engine_train.py:60-63, one step ahead on a side stream), the module is
-    # called under autocast, `loss.item()` reads the loss back and the step ends with torch.cuda.synchronize(), exactly
-    # like engine_train.py:65-93.  A second, pipelined variant (loss read deferred by one step) is reported next to it.
+    # strict = engine_train.train_one_epoch verbatim (engine_train.py:52-93): every step copies its batch from pinned
+    # host memory with .to(device, non_blocking=True) on the compute stream, calls the module under autocast, reads
+    # the loss with loss.item(), runs backward + the optimizer step and ends with torch.cuda.synchronize().
+    # pipelined = the same work with painter_b200.data_utils.DevicePrefetcher issuing the copies one step ahead on a
+    # side stream and each step's loss read back one step later (no per-step drain) - reported next to it.
     from painter_b200.data_utils import DevicePrefetcher
 
-    def run_e2e(strict):
+    def run_e2e(strict, n):
         seen = []
-        losses = torch.empty(args.steps, dtype=torch.float32).pin_memory()
+        losses = torch.empty(max(n, 1), dtype=torch.float32).pin_memory()
         sync()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         prev = None
-        for i, batch in enumerate(DevicePrefetcher((host for _ in range(args.steps)), dev)):
+        src = ([t.to(dev, non_blocking=True) for t in host] for _ in range(n)) if strict else \
+            DevicePrefetcher((host for _ in range(n)), dev)
+        for i, batch in enumerate(src):
             imgs, tgts, mask, valid = batch
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 loss, _, _ = net(imgs, tgts, bool_masked_pos=mask, valid=valid)
@@ -538,8 +559,10 @@ def main():
         sync()
         return a.elapsed_time(b), seen
 
-    ms_e2e, seen = run_e2e(True)
-    ms_e2e_pipe, _ = run_e2e(False)
+    run_e2e(True, 2)        # untimed: first-use costs of the loop (stream / buffer creation) are not steady state
+    run_e2e(False, 2)
+    ms_e2e, seen = run_e2e(True, args.steps)
+    ms_e2e_pipe, _ = run_e2e(False, args.steps)
     last_loss = seen[-1]
     clk = clocks.stop() if rank == 0 else None
 
@@ -586,10 +609,11 @@ def main():
                              "no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
-                    "loop": "engine_train.train_one_epoch's: pinned-host batch -> device every step (prefetched one "
-                            "step ahead on a side stream), loss.item() and torch.cuda.synchronize() every step",
+                    "loop": "engine_train.train_one_epoch's (engine_train.py:52-93): pinned-host batch .to(device, "
+                            "non_blocking=True) on the compute stream, loss.item() and torch.cuda.synchronize() every step",
                     "pipelined_value": world * B / (ms_e2e_pipe / args.steps / 1e3),
-                    "pipelined_note": "same, but each step's loss is read back one step later (no per-step drain)"},
+                    "pipelined_note": "same work with data_utils.DevicePrefetcher (copies one step ahead on a side "
+                                      "stream) and each step's loss read back one step later (no per-step drain)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "pk::gemm_bf16_kernel (tcgen05 GEMM, all linear layers fwd/bwd)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -232,6 +232,32 @@ int pk_nearest_blend(const double* seg, int SH, int SW, const uint8_t* image, ui
                      void* stream);
 int pk_bilinear_u8(const double* seg, int SH, int SW, uint8_t* dst, int OH, int OW, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32-accurate forward mode (north star: within 1e-5 of the reference's fp32 forward, the way
+ * seggpt_engine.run_one_image calls the model, seggpt_engine.py:47).  Every fp32 GEMM operand is split into three
+ * bf16 terms (h, m, l) and the six significant cross products are evaluated by ONE pk_gemm_bf16 call over operands
+ * concatenated along K: A' = [l|m|h|m|h|h], B' = [h|m|l|h|m|h] (K' = 6K, fp32 accumulation in TMEM).
+ *  pk_split3                 out bf16 [M, 6K] from x fp32 [M, K] (side_b: 0 = A-side, 1 = B-side order); gelu != 0
+ *                            applies the exact erf GELU (timm Mlp act, models_painter.py:201) first
+ *  pk_split3_heads           q / k / v of qkv fp32 [B*N, 3C] -> per-(b, head) operands of the attention GEMMs
+ *                            (which: 0 q [B*heads, N, 384]; 1 k [B*heads, Npad, 384]; 2 v [B*heads, 6*Npad, 64])
+ *  pk_softmax_relpos_split3  P' = split(softmax(scale * S + rel_h + rel_w)) (models_painter.py:80-86,
+ *                            vitdet_utils.py:113-123) from S fp32 [BH, N, Npad], Gh = q.T_h^T, Gw = q.T_w^T
+ *  pk_im2col_patch_split3    PatchEmbed im2col of imgs and tgts (vitdet_utils.py:178-186) as split A operand
+ *  pk_dec_im2col_split3      pixel shuffle + 3x3 im2col of decoder_embed's output (models_painter.py:424-430)
+ *  pk_head_f32               LayerNorm2D + exact GELU + conv1x1 + masked loss terms + patchify, fp32, from the fp32
+ *                            conv3x3 output [B*H*W, 64]; num accumulates in fp64 (num_zeroed) and is emitted as fp32  */
+int pk_split3(const float* x, int ldx, void* out_bf16, int M, int K, int side_b, int gelu, void* stream);
+int pk_split3_heads(const float* qkv, void* out_bf16, int B, int heads, int N, int Npad, int which, void* stream);
+int pk_softmax_relpos_split3(const float* S, const float* Gh, int ldgh, const float* Gw, int ldgw, void* P_bf16,
+                             int BH, int N, int Npad, int h, int w, float scale, void* stream);
+int pk_im2col_patch_split3(const float* imgs, const float* tgts, void* out_bf16, int B, int Cin, int H, int W, int p,
+                           void* stream);
+int pk_dec_im2col_split3(const float* D, void* out_bf16, int B, int h, int w, int p, int dd, void* stream);
+int pk_head_f32(const float* c1, const float* head_params, const float* tgts, const uint8_t* mask, int maskB,
+                const float* valid, float* patch, double* num_zeroed, float* num_out, int B, int H, int W, int p,
+                int loss_kind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,6 +256,208 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ c1, const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// head_bwd2_kernel: the same math with a LANE PAIR per pixel (each lane owns 32 of the pixel's 64 channels in
+// registers: LayerNorm statistics, the 1x1 convolution and its transpose cost 7 pair-shuffles per pixel instead of 35
+// warp-wide ones) and the per-channel parameter gradients reduced over the 16 pixels of a warp with a butterfly
+// transpose-reduce (30 shuffles per quantity: afterwards lane l holds channels 32 (l & 1) + 2 (l >> 1) + {0, 1} summed
+// over the warp's pixels).  Head parameters are staged once per block in shared memory as {gamma, beta, w0, w1}, {w2}
+// records (two broadcast LDS.128 per channel); no global or __constant__ state.
+// ---------------------------------------------------------------------------------------------
+// v[32] per lane, reduced over the 16 lanes of equal parity; result v[0], v[1] (see above)
+__device__ __forceinline__ void transpose_reduce_pairs(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 2; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+__device__ __forceinline__ float pair_sum(float v) { return v + __shfl_xor_sync(0xffffffffu, v, 1); }
+// volatile shared-memory load of one parameter record: keeps ptxas from hoisting all 64 records of a pass into
+// registers (which cost 160 registers and spills); the loads are warp-uniform broadcasts, two per channel
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(128, 2)
+head_bwd2_kernel(const __nv_bfloat16* __restrict__ c1, const float* __restrict__ tgts,
+                 const uint8_t* __restrict__ mask, int maskB, const float* __restrict__ valid,
+                 const float* __restrict__ coef, const float* __restrict__ gscale, const float* __restrict__ hp,
+                 __nv_bfloat16* __restrict__ dc1, float* __restrict__ dhp, int B, int H, int W, int p, int loss_kind,
+                 int pix_per_warp) {
+  __shared__ float4 prm[64][2];     // [k] = {gamma, beta, w0, w1}, {w2, -, -, -}
+  __shared__ float red[4][323];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int hsel = lane & 1, kb = hsel * 32;
+  for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+    prm[k][0] = make_float4(hp[64 + k], hp[128 + k], hp[192 + k], hp[256 + k]);
+    prm[k][1] = make_float4(hp[320 + k], 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const float b1_0 = hp[384], b1_1 = hp[385], b1_2 = hp[386];
+  const uint32_t prm_s = smem_u32(&prm[0][0]) + static_cast<uint32_t>(kb) * 32u;   // this lane's 32 records
+  const float gs = gscale ? gscale[0] : 1.f;
+  const int wt = W / p, Ntok = (H / p) * wt;
+  const uint32_t plane = static_cast<uint32_t>(H) * W;
+  const uint32_t npix = static_cast<uint32_t>(B) * plane;
+  float acc[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};   // dgamma, dbeta, dW0, dW1, dW2 of this lane's channels
+  float db0 = 0.f, db1v = 0.f, db2 = 0.f;
+  const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + wq;
+  const uint32_t base0 = warp_global * static_cast<uint32_t>(pix_per_warp);
+  for (int it = 0; it < pix_per_warp; it += 16) {
+    const uint32_t pix = base0 + it + (lane >> 1);
+    const bool live = pix < npix;
+    const uint32_t pc = live ? pix : npix - 1;
+    uint32_t raw[16];
+    const uint4* src = reinterpret_cast<const uint4*>(c1 + static_cast<size_t>(pc) * 64 + kb);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = src[q];
+      raw[4 * q] = u.x; raw[4 * q + 1] = u.y; raw[4 * q + 2] = u.z; raw[4 * q + 3] = u.w;
+    }
+    const uint32_t bq = pc / plane, yx = pc - bq * plane;
+    const uint32_t yq = yx / static_cast<uint32_t>(W), xq = yx - yq * static_cast<uint32_t>(W);
+    const float mk = mask[static_cast<size_t>(bq % maskB) * Ntok + (yq / p) * wt + xq / p] ? 1.f : 0.f;
+    float tg[3], vl[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t o = (static_cast<size_t>(bq) * 3 + c) * plane + yx;
+      tg[c] = tgts[o];
+      vl[c] = valid[o];
+    }
+    const float cf = live ? gs * coef[bq] * mk : 0.f;
+#define HB2_X(j) (((j) & 1) ? __uint_as_float(raw[(j) >> 1] & 0xFFFF0000u) : __uint_as_float(raw[(j) >> 1] << 16))
+    // ---- statistics over the pixel's 64 channels (32 here + 32 in the partner lane)
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mean += HB2_X(j);
+    mean = pair_sum(mean) * (1.f / 64);
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = HB2_X(j) - mean;
+      var += a * a;
+    }
+    const float rstd = rsqrtf(pair_sum(var) * (1.f / 64) + 1e-6f);
+    // ---- forward: gelu(ln) of this lane's channels, pred_c
+    float ge[32];
+    float pr0 = 0.f, pr1 = 0.f, pr2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float4 p0 = lds_v4(prm_s + j * 32);
+      const float w2 = lds_f(prm_s + j * 32 + 16);
+      const float g = gelu_erf(p0.x * ((HB2_X(j) - mean) * rstd) + p0.y);
+      ge[j] = g;
+      pr0 += p0.z * g;
+      pr1 += p0.w * g;
+      pr2 += w2 * g;
+    }
+    float dp[3];
+    {
+      const float prd[3] = {pair_sum(pr0) + b1_0, pair_sum(pr1) + b1_1, pair_sum(pr2) + b1_2};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d = prd[c] - tg[c];
+        float dl;
+        if (loss_kind == 0) dl = fminf(fmaxf(d * 100.f, -1.f), 1.f);
+        else if (loss_kind == 1) dl = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        else if (loss_kind == 2) dl = 2.f * d;
+        else dl = 0.5f * ((d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) + 2.f * d);
+        dp[c] = cf * vl[c] * dl;
+      }
+    }
+    if (hsel == 0) {
+      db0 += dp[0];
+      db1v += dp[1];
+      db2 += dp[2];
+    }
+    // ---- backward through 1x1, GELU, LayerNorm2D
+    float t[32];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {      // dW_c[k] += dp_c * gelu(ln_k)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = ge[j] * dp[c];
+      transpose_reduce_pairs(t, lane);
+      acc[2 + c][0] += t[0];
+      acc[2 + c][1] += t[1];
+    }
+    float dln[32];
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float4 p0 = lds_v4(prm_s + j * 32);
+      const float w2 = lds_f(prm_s + j * 32 + 16);
+      const float xh = (HB2_X(j) - mean) * rstd;
+      const float d = (dp[0] * p0.z + dp[1] * p0.w + dp[2] * w2) * gelu_erf_grad(p0.x * xh + p0.y);
+      dln[j] = d;
+      const float dx = d * p0.x;
+      a1 += dx;
+      a2 += dx * xh;
+      t[j] = d * xh;
+    }
+    transpose_reduce_pairs(t, lane);    // dgamma
+    acc[0][0] += t[0];
+    acc[0][1] += t[1];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = dln[j];
+    transpose_reduce_pairs(t, lane);    // dbeta
+    acc[1][0] += t[0];
+    acc[1][1] += t[1];
+    a1 = pair_sum(a1) * (1.f / 64);
+    a2 = pair_sum(a2) * (1.f / 64);
+    if (live) {
+      uint4* dst = reinterpret_cast<uint4*>(dc1 + static_cast<size_t>(pix) * 64 + kb);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = q * 8 + e * 2;
+          const float x0 = (HB2_X(j) - mean) * rstd, x1 = (HB2_X(j + 1) - mean) * rstd;
+          o[e] = pack_bf16x2(rstd * (dln[j] * lds_f(prm_s + j * 32) - a1 - x0 * a2),
+                             rstd * (dln[j + 1] * lds_f(prm_s + (j + 1) * 32) - a1 - x1 * a2));
+        }
+        dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+#undef HB2_X
+  }
+  db0 = warp_sum(db0);
+  db1v = warp_sum(db1v);
+  db2 = warp_sum(db2);
+  {
+    const int k0 = kb + 2 * (lane >> 1);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      red[wq][k0 + e] = acc[0][e];
+      red[wq][64 + k0 + e] = acc[1][e];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) red[wq][128 + c * 64 + k0 + e] = acc[2 + c][e];
+    }
+  }
+  if (lane == 0) {
+    red[wq][320] = db0; red[wq][321] = db1v; red[wq][322] = db2;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 323; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < 4; ++w) s += red[w][i];
+    atomicAdd(dhp + 64 + i, s);
+  }
+}
+
 // conv bias gradient: db[o] = sum_pix dC1[pix, o]  (bf16 [npix, 64])  -> reuse the generic column sum
 }  // namespace pk
 
@@ -290,6 +492,9 @@ extern "C" int pk_loss_finalize(const float* stats, const float* num, float* los
   PK_LAUNCH_CHECK("pk_loss_finalize");
   return 0;
 }
+static int g_head_bwd_legacy = 0;
+// test hook: 1 = the warp-per-pixel kernel of round 1 (kept as an independent implementation to cross-check)
+extern "C" void pk_head_bwd_legacy(int on) { g_head_bwd_legacy = on; }
 extern "C" int pk_decoder_head_bwd(const void* c1, const float* tgts, const uint8_t* mask, int maskB,
                                    const float* valid, const float* coef, const float* gscale,
                                    const float* head_params, void* dc1, float* dhead_params_zeroed, int B,
@@ -298,10 +503,24 @@ extern "C" int pk_decoder_head_bwd(const void* c1, const float* tgts, const uint
            "pk_decoder_head_bwd: null pointer");
   PK_CHECK(W % 4 == 0 && static_cast<long long>(B) * H * W < (1ll << 31),
            "pk_decoder_head_bwd: W must be a multiple of 4 and B*H*W < 2^31");
-  const int grid = sm_count() * 4;
-  head_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(c1), tgts, mask, maskB, valid, coef, gscale, head_params,
-      static_cast<__nv_bfloat16*>(dc1), dhead_params_zeroed, B, H, W, p, loss_kind);
+  if (g_head_bwd_legacy) {
+    const int grid = sm_count() * 4;
+    head_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(c1), tgts, mask, maskB, valid, coef, gscale, head_params,
+        static_cast<__nv_bfloat16*>(dc1), dhead_params_zeroed, B, H, W, p, loss_kind);
+  } else {
+    // a lane pair per pixel; every warp walks `ppw` consecutive pixels (a multiple of 16) so that the block-level
+    // parameter-gradient atomics stay ~4 per SM-resident block
+    const long long npix = static_cast<long long>(B) * H * W;
+    const long long warps_target = static_cast<long long>(sm_count()) * 16;
+    long long ppw = (npix + warps_target - 1) / warps_target;
+    ppw = (ppw + 15) / 16 * 16;
+    const long long warps = (npix + ppw - 1) / ppw;
+    const int grid = static_cast<int>((warps + 3) / 4);
+    head_bwd2_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(c1), tgts, mask, maskB, valid, coef, gscale, head_params,
+        static_cast<__nv_bfloat16*>(dc1), dhead_params_zeroed, B, H, W, p, loss_kind, static_cast<int>(ppw));
+  }
   PK_LAUNCH_CHECK("pk_decoder_head_bwd");
   return 0;
 }

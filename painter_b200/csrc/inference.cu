@@ -47,7 +47,7 @@ stitch_normalize_kernel(const CanvasSrc src, float* __restrict__ out, int P, int
     const size_t sidx = (static_cast<size_t>(yy) * S + x) * 3 + c;
     const double v = is_top ? load_unit(src.top[p], src.top_dtype[p], sidx)
                             : load_unit(src.bottom[p], src.bottom_dtype[p], sidx);
-    out[i] = static_cast<float>((v - c_mean[c]) / c_std[c]);
+    out[i] = static_cast<float>(__dsub_rn(v, c_mean[c]) / c_std[c]);
   }
 }
 
@@ -84,7 +84,8 @@ seg_postprocess_kernel(const float* __restrict__ patch, double* __restrict__ out
     double s = 0.0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      double v = (static_cast<double>(src[c]) * c_std[c] + c_mean[c]) * 255.0;
+      // explicit IEEE mul / add: numpy rounds the product before the addition (no fused multiply-add)
+      double v = __dmul_rn(__dadd_rn(__dmul_rn(static_cast<double>(src[c]), c_std[c]), c_mean[c]), 255.0);
       v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);
       out[i * 3 + c] = v;
       s += v;
@@ -114,7 +115,7 @@ nearest_blend_kernel(const double* __restrict__ seg, int SH, int SW, const uint8
     const int x = static_cast<int>(r % OW), y = static_cast<int>(r / OW);
     const int sy = nearest_idx(y, SH, OH), sx = nearest_idx(x, SW, OW);
     const double o = seg[(static_cast<size_t>(sy) * SW + sx) * 3 + c];
-    const double v = static_cast<double>(image[i]) * (0.6 * o / 255.0 + 0.4);
+    const double v = __dmul_rn(static_cast<double>(image[i]), __dadd_rn(__dmul_rn(0.6, o) / 255.0, 0.4));
     dst[i] = static_cast<uint8_t>(v);   // numpy astype(uint8): truncation (values are within [0, 255])
   }
 }

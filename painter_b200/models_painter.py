@@ -99,6 +99,11 @@ class LayerNorm2D(nn.Module):
 
 class Painter(nn.Module):
     seggpt = False
+    # arithmetic of forward: "bf16" (tensor-core operands in bf16, fp32 accumulate - the training mode), "fp32"
+    # (fp32-accurate split-operand mode, painter_b200/accurate.py, forward only) or "auto": fp32-accurate when the
+    # module is called the way the reference's inference code calls it - outside autocast, gradients disabled
+    # (seggpt_engine.py:26,47) - and bf16 otherwise (engine_train.py:65 runs under autocast)
+    precision = "auto"
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=1024, depth=24, num_heads=16,
                  mlp_ratio=4., qkv_bias=True, drop_path_rate=0., norm_layer=nn.LayerNorm, act_layer=nn.GELU,
@@ -258,6 +263,16 @@ class Painter(nn.Module):
             valid = valid.expand_as(tgts).contiguous()
         mask_u8 = bool_masked_pos.reshape(-1, N).to(torch.uint8).contiguous()
         assert mask_u8.shape[0] in (1, B), "bool_masked_pos must have batch 1 or B"
+        prec = self.precision
+        if prec not in ("auto", "bf16", "fp32"):
+            raise ValueError(f"painter_b200: precision must be 'auto', 'bf16' or 'fp32', got {prec!r}")
+        if prec == "fp32" or (prec == "auto" and not torch.is_autocast_enabled("cuda") and
+                              not torch.is_grad_enabled()):
+            if self.training and any(b.drop_prob > 0 for b in self.blocks):
+                raise NotImplementedError("painter_b200: the fp32-accurate mode is an inference mode (call .eval())")
+            from . import accurate
+            return accurate.forward(self, imgs, tgts, mask_u8, valid, self._type_emb(B, seg_type, dev),
+                                    merge_between_batch)
         pe = self.patch_embed.proj
         # gradient arena + per-step token (engine.StageEnv): only when this forward can be followed by a backward
         arena = get_arena(self) if torch.is_grad_enabled() else None

@@ -13,8 +13,9 @@ def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name), weights_only=False)
 
 
-def build_model(cfg: po.PainterConfig, seed, device="cuda"):
-    """painter_b200 module of the same geometry as `cfg`, loaded with the synthetic reference-format weights."""
+def build_model(cfg: po.PainterConfig, seed, device="cuda", precision="bf16"):
+    """painter_b200 module of the same geometry as `cfg`, loaded with the synthetic reference-format weights.
+    precision: the module's arithmetic mode, pinned to "bf16" unless a test is about the fp32-accurate / auto modes."""
     from functools import partial
     from painter_b200 import models_painter, models_seggpt
     cls = models_seggpt.SegGPT if cfg.seggpt else models_painter.Painter
@@ -26,6 +27,7 @@ def build_model(cfg: po.PainterConfig, seed, device="cuda"):
             pretrain_img_size=cfg.pretrain_img_size)
     sd = synth_state_dict(cfg, seed)
     m.load_state_dict(sd, strict=True)
+    m.precision = precision
     return m.to(device), sd
 
 

@@ -337,6 +337,13 @@ def test_decoder_head_loss_and_gradients(seggpt):
     (rl * 3.0).backward()
     gscale = torch.tensor([3.0], device=DEV)
     dc1, dhp = ops.decoder_head_bwd(c1, tgts, mu8, valid, coef, gscale, hp, p, 0)
+    # the lane-pair kernel against round 1's independent warp-per-pixel implementation (same math, different
+    # reduction trees): parameter gradients to fp32 summation noise, dC1 to one bf16 ulp
+    from painter_b200._lib import lib
+    lib().pk_head_bwd_legacy(1)
+    dc1_l, dhp_l = ops.decoder_head_bwd(c1, tgts, mu8, valid, coef, gscale, hp, p, 0)
+    lib().pk_head_bwd_legacy(0)
+    assert relmax(dhp[64:387], dhp_l[64:387]) < 1e-4 and relmax(dc1, dc1_l) < 1e-2
     assert relmax(dhp[64:128], leaves[3].grad) < 3e-2 and relmax(dhp[128:192], leaves[4].grad) < 3e-2
     assert relmax(dhp[192:384].view(3, 64, 1, 1), leaves[5].grad) < 3e-2 and relmax(dhp[384:387], leaves[6].grad) < 3e-2
     assert relmax(ops.colsum_bf16(dc1.view(-1, 64)), leaves[2].grad) < 3e-2

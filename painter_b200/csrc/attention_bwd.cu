@@ -420,62 +420,47 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t tS_h = tS + (j & 1) * 224 + lane_addr + cbase, tdP_h = tS_h + 112;
       const uint32_t sdS_j = sdS + (j & 1) * 32768;
       if (j >= 2) mbar_wait(bar_df + 8 * (j & 1), ((j >> 1) - 1) & 1);  // dQ(j-2) has drained this dS buffer
-      // 56 columns per thread: 16 + 16 + 16 + 8
+      // 56 columns per thread as 7 chunks of 8, software-pipelined: the TMEM loads of chunk ci + 1 are in flight
+      // while chunk ci is processed (two softmax warps per scheduler cannot hide a tcgen05.ld round trip per chunk)
+      uint32_t v[2][8], w[2][8];
+      tmem_ld_x8(tS_h, v[0]);
+      tmem_ld_x8(tdP_h, w[0]);
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c0 = ci * 16;
-        const int nc = ci < 3 ? 16 : 8;
-        uint32_t v[16], w[16];
-        if (ci < 3) {
-          tmem_ld_x16(tS_h + c0, v);
-          tmem_ld_x16(tdP_h + c0, w);
-        } else {
-          uint32_t v8[8], w8[8];
-          tmem_ld_x8(tS_h + c0, v8);
-          tmem_ld_x8(tdP_h + c0, w8);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            v[c] = v8[c];
-            w[c] = w8[c];
-          }
-        }
+      for (int ci = 0; ci < 7; ++ci) {
+        const int c0 = ci * 8;
         tmem_wait_ld();
-        uint32_t dsb[8];
-#pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          if (c < nc) {
-            const int kc = c0 + c;
-            float d0, d1;
-            if constexpr (PK2) {
-              const f32x2 t2 = fma_f2(pack_u2(v[c], v[c + 1]), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2]));
-              float t0, t1;
-              unpack_f2(t2, t0, t1);
-              const f32x2 d2 = mul_f2(pack_f2(fast_exp2(t0), fast_exp2(t1)), add_f2(pack_u2(w[c], w[c + 1]), nd2));
-              gh2[kc / W] = add_f2(gh2[kc / W], d2);
-              gw2[(kc % W) / 2] = add_f2(gw2[(kc % W) / 2], d2);
-              unpack_f2(d2, d0, d1);
-            } else {
-              const int k1 = kc + 1;
-              d0 = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W])) *
-                   (__uint_as_float(w[c]) - delta);
-              d1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sc, hb[k1 / W] + relw[k1 % W])) *
-                   (__uint_as_float(w[c + 1]) - delta);
-              gh[kc / W] += d0;
-              gh[k1 / W] += d1;
-              gw[kc % W] += d0;
-              gw[k1 % W] += d1;
-            }
-            dsb[c / 2] = pack_bf16x2(d0, d1);
-          }
+        if (ci + 1 < 7) {
+          tmem_ld_x8(tS_h + c0 + 8, v[(ci + 1) & 1]);
+          tmem_ld_x8(tdP_h + c0 + 8, w[(ci + 1) & 1]);
         }
+        uint32_t dsb[4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q * 8 < nc) {
-            const int g8 = ((cbase + c0) >> 3) + q;  // 8-column group inside the 112-wide tile
-            st_shared_v4(sdS_j + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4), dsb[q * 4 + 0],
-                         dsb[q * 4 + 1], dsb[q * 4 + 2], dsb[q * 4 + 3]);
+        for (int c = 0; c < 8; c += 2) {
+          const int kc = c0 + c;
+          const uint32_t v0 = v[ci & 1][c], v1 = v[ci & 1][c + 1], w0 = w[ci & 1][c], w1 = w[ci & 1][c + 1];
+          float d0, d1;
+          if constexpr (PK2) {
+            const f32x2 t2 = fma_f2(pack_u2(v0, v1), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2]));
+            float t0, t1;
+            unpack_f2(t2, t0, t1);
+            const f32x2 d2 = mul_f2(pack_f2(fast_exp2(t0), fast_exp2(t1)), add_f2(pack_u2(w0, w1), nd2));
+            gh2[kc / W] = add_f2(gh2[kc / W], d2);
+            gw2[(kc % W) / 2] = add_f2(gw2[(kc % W) / 2], d2);
+            unpack_f2(d2, d0, d1);
+          } else {
+            const int k1 = kc + 1;
+            d0 = fast_exp2(fmaf(__uint_as_float(v0), sc, hb[kc / W] + relw[kc % W])) * (__uint_as_float(w0) - delta);
+            d1 = fast_exp2(fmaf(__uint_as_float(v1), sc, hb[k1 / W] + relw[k1 % W])) * (__uint_as_float(w1) - delta);
+            gh[kc / W] += d0;
+            gh[k1 / W] += d1;
+            gw[kc % W] += d0;
+            gw[k1 % W] += d1;
           }
+          dsb[c / 2] = pack_bf16x2(d0, d1);
         }
+        const int g8 = (cbase + c0) >> 3;  // 8-column group inside the 112-wide tile
+        st_shared_v4(sdS_j + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4), dsb[0], dsb[1], dsb[2],
+                     dsb[3]);
       }
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
@@ -843,47 +828,36 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (i >= 2) mbar_wait(bar_pe + 8 * (i & 1), ((i >> 1) - 1) & 1);  // dV(i-2) has drained this P buffer
       // ---- pass 1: p = exp2(scale * S + bias - lse) (fp32, kept in registers for pass 2), P -> smem as bf16 ----
       f32x2 pp[AB_KT / 4];   // 56 probabilities as 28 packed pairs
+      {
+        uint32_t v[2][8];   // 7 chunks of 8 columns, TMEM loads one chunk ahead (see kernel A)
+        tmem_ld_x8(tS_h, v[0]);
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c0 = ci * 16;
-        const int nc = ci < 3 ? 16 : 8;
-        uint32_t v[16];
-        if (ci < 3) {
-          tmem_ld_x16(tS_h + c0, v);
-        } else {
-          uint32_t v8[8];
-          tmem_ld_x8(tS_h + c0, v8);
+        for (int ci = 0; ci < 7; ++ci) {
+          const int c0 = ci * 8;
+          tmem_wait_ld();
+          if (ci + 1 < 7) tmem_ld_x8(tS_h + c0 + 8, v[(ci + 1) & 1]);
+          uint32_t pb[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = v8[c];
-        }
-        tmem_wait_ld();
-        uint32_t pb[8];
-#pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          if (c < nc) {
+          for (int c = 0; c < 8; c += 2) {
             const int kc = c0 + c;
+            const uint32_t v0 = v[ci & 1][c], v1 = v[ci & 1][c + 1];
             float p0, p1;
             if constexpr (PK2) {
               float t0, t1;
-              unpack_f2(fma_f2(pack_u2(v[c], v[c + 1]), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2])), t0, t1);
+              unpack_f2(fma_f2(pack_u2(v0, v1), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2])), t0, t1);
               p0 = fast_exp2(t0);
               p1 = fast_exp2(t1);
             } else {
               const int k1 = kc + 1;
-              p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sc, hb[kc / W] + relw[kc % W]));
-              p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sc, hb[k1 / W] + relw[k1 % W]));
+              p0 = fast_exp2(fmaf(__uint_as_float(v0), sc, hb[kc / W] + relw[kc % W]));
+              p1 = fast_exp2(fmaf(__uint_as_float(v1), sc, hb[k1 / W] + relw[k1 % W]));
             }
             pp[kc / 2] = pack_f2(p0, p1);
             pb[c / 2] = pack_bf16x2(p0, p1);
           }
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q * 8 < nc) {
-            const int g8 = ((cbase + c0) >> 3) + q;
-            const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
-            st_shared_v4(sP_i + off, pb[q * 4 + 0], pb[q * 4 + 1], pb[q * 4 + 2], pb[q * 4 + 3]);
-          }
+          const int g8 = (cbase + c0) >> 3;
+          const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
+          st_shared_v4(sP_i + off, pb[0], pb[1], pb[2], pb[3]);
         }
       }
       // S(i) is consumed: its TMEM buffer may take dP(i+1)
@@ -895,44 +869,33 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 1);
       tc_fence_after();
       if (i >= 1) mbar_wait(bar_dsf, (i - 1) & 1);   // the dK MMAs of tile i-1 have drained the dS buffer
+      {
+        uint32_t w[2][8];
+        tmem_ld_x8(tdP_h, w[0]);
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c0 = ci * 16;
-        const int nc = ci < 3 ? 16 : 8;
-        uint32_t w[16];
-        if (ci < 3) {
-          tmem_ld_x16(tdP_h + c0, w);
-        } else {
-          uint32_t w8[8];
-          tmem_ld_x8(tdP_h + c0, w8);
+        for (int ci = 0; ci < 7; ++ci) {
+          const int c0 = ci * 8;
+          tmem_wait_ld();
+          if (ci + 1 < 7) tmem_ld_x8(tdP_h + c0 + 8, w[(ci + 1) & 1]);
+          uint32_t dsb[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) w[c] = w8[c];
-        }
-        tmem_wait_ld();
-        uint32_t dsb[8];
-#pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          if (c < nc) {
+          for (int c = 0; c < 8; c += 2) {
             const int kc = c0 + c;
+            const uint32_t w0 = w[ci & 1][c], w1 = w[ci & 1][c + 1];
             float d0, d1;
             if constexpr (PK2) {
-              unpack_f2(mul_f2(pp[kc / 2], add_f2(pack_u2(w[c], w[c + 1]), nd2)), d0, d1);
+              unpack_f2(mul_f2(pp[kc / 2], add_f2(pack_u2(w0, w1), nd2)), d0, d1);
             } else {
               float p0, p1;
               unpack_f2(pp[kc / 2], p0, p1);
-              d0 = p0 * (__uint_as_float(w[c]) - delta);
-              d1 = p1 * (__uint_as_float(w[c + 1]) - delta);
+              d0 = p0 * (__uint_as_float(w0) - delta);
+              d1 = p1 * (__uint_as_float(w1) - delta);
             }
             dsb[c / 2] = pack_bf16x2(d0, d1);
           }
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q * 8 < nc) {
-            const int g8 = ((cbase + c0) >> 3) + q;
-            const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
-            st_shared_v4(sdS_i + off, dsb[q * 4 + 0], dsb[q * 4 + 1], dsb[q * 4 + 2], dsb[q * 4 + 3]);
-          }
+          const int g8 = (cbase + c0) >> 3;
+          const uint32_t off = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
+          st_shared_v4(sdS_i + off, dsb[0], dsb[1], dsb[2], dsb[3]);
         }
       }
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 2);

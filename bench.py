@@ -165,6 +165,49 @@ def cpu_reference_step_time(threads, reps=1, budget_s=None, min_reps=1):
     return times, kind
 
 
+def reference_cuda_eager(dev, host, steps):
+    """BASELINE.md section 3 "the practical bar to beat": the UNMODIFIED reference module in stock torch-CUDA eager on
+    the same GPU - torch.autocast(bf16), same batch, forward + backward + torch's fused AdamW.  A labelled comparator
+    next to the headline (the contract's reference arm stays the CPU path); baseline leg only, never on our path."""
+    import torch
+    from oracle import painter_oracle as po
+    from oracle import ref_loader
+    from oracle.synth import synth_state_dict
+    if not ref_loader.available():
+        return {"unavailable": "reference tree not staged (scripts/stage_reference.py)"}
+    torch.cuda.empty_cache()
+    model = ref_loader.models_painter().painter_vit_large_patch16_input896x448_win_dec64_8glb_sl1()
+    model.load_state_dict(synth_state_dict(po.PainterConfig(), 0), strict=True)
+    model = model.to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05, fused=True)
+    batch = [t.to(dev) for t in host]
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, _, _ = model(batch[0], batch[1], bool_masked_pos=batch[2], valid=batch[3].clone())
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    n = max(2, min(steps, 5))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"value": batch[0].shape[0] / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "steps": n,
+            "what": "unmodified reference module, stock torch-CUDA eager (cuBLAS / cuDNN / ATen), torch.autocast(bf16), "
+                    "same batch, fwd + bwd + torch fused AdamW, same GPU", "peak_mem_gib": round(peak_gb, 1)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -624,6 +667,10 @@ def main():
             "clocks": clk, "loss": last_loss,
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "train":
+            try:
+                line["reference_cuda_eager"] = reference_cuda_eager(dev, host, args.steps)
+            except Exception as ex:      # a labelled extra: never let it take the bench line down
+                line["reference_cuda_eager"] = {"error": repr(ex)[:200]}
             threads = min(os.cpu_count() or 1, 32)
             ts, kind = cpu_reference_step_time(threads, reps=2)
             line["cpu_baseline"] = {"value": 1.0 / ts[-1], "unit": "images/s", "cores": threads, "kind": kind,

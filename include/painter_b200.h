@@ -258,6 +258,20 @@ int pk_head_f32(const float* c1, const float* head_params, const float* tgts, co
                 const float* valid, float* patch, double* num_zeroed, float* num_out, int B, int H, int W, int p,
                 int loss_kind, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training data path, per-sample device work.
+ *  pk_block_masks  BEiT block masks, one warp per sample: Painter/util/masking_generator.py:15-93 (blocks of random
+ *                  area / log-uniform aspect ratio until num_masking cells are covered, then an exact-count fix-up) and
+ *                  the half-mask alternative of Painter/data/pairdataset.py:149,183-186.  out int32 [B, H, W].
+ *  pk_valid_maps   the per-task loss-weight maps of pairdataset.py:154-181.  rule[b]: 0 all ones; 1 valid[t < thr] = 0
+ *                  (depth / semantic / panoptic-semantic); 2 valid[t > thr] = 10 and all 0 when fewer than 300
+ *                  foreground values (pose); 3 all 0 when fewer than 300 foreground values (panoptic instances).
+ *                  thr: fp32 [B, 3] normalised thresholds; fg_zeroed: int32 [B] scratch.                          */
+int pk_block_masks(int* out, int B, int H, int W, int num_masking, int min_patches, int max_patches, float log_ar_lo,
+                   float log_ar_hi, float half_mask_ratio, unsigned long long seed, void* stream);
+int pk_valid_maps(const float* targets, const int* rule_dev, const float* thr_dev, int* fg_zeroed, float* valid, int B,
+                  int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,8 +42,6 @@ struct AttnFwdArgs {
   int ldo;
   float* lse;             // [B*heads, N]  (log2 domain: m + log2(l))
   long long* trace;       // optional debug timeline (CTA 0 only): [role][tile][event] clock64 stamps
-  int stagger_ns;         // first wave: CTAs landing in an SM's second slot start this much later (see kernel)
-  int sm_count;
 };
 
 // debug timeline: role 0 = producer, 1 = MMA issuer, 2 = softmax row 0; 8 events per tile
@@ -81,19 +79,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int head = blockIdx.y, b = blockIdx.z;
   const int C = a.heads * 64;
   const int num_tiles = (a.h + R - 1) / R;
-  // Two CTAs share an SM.  Launched together they run in lock step - both in their softmax phase (contending for
-  // the MUFU pipe), then both waiting on their MMAs - so neither unit is ever busy while the other is.  Delaying the
-  // CTAs that fill the SMs' second slots in the first wave by about half a tile period puts the pair in anti-phase;
-  // every CTA lives equally long, so replacements inherit the offset for the rest of the grid.
-  if (a.stagger_ns > 0) {
-    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    if (lin >= static_cast<unsigned>(a.sm_count) && lin < 2u * a.sm_count) {
-      const uint64_t t0 = globaltimer_ns();
-      while (globaltimer_ns() - t0 < static_cast<uint64_t>(a.stagger_ns)) {
-      }
-    }
-  }
-
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
@@ -430,9 +415,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 using namespace pk;
 
 static long long* g_attn_trace = nullptr;
-static int g_attn_stagger_ns = 0;
-// tuning hook: start delay (ns) of the first wave's second-slot CTAs of pk_attn_fwd (0 = off)
-extern "C" void pk_attn_fwd_stagger(int ns) { g_attn_stagger_ns = ns; }
+
 // debug hook: device buffer of 3*16*8 int64 receiving a clock64 timeline of CTA (0,0,0); nullptr disables
 extern "C" void pk_attn_set_trace(void* buf) { g_attn_trace = static_cast<long long*>(buf); }
 
@@ -461,8 +444,6 @@ extern "C" int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void
   a.ldo = C;
   a.lse = lse;
   a.trace = g_attn_trace;
-  a.stagger_ns = g_attn_stagger_ns;
-  a.sm_count = sm_count();
 
   CUtensorMap tmQ, tmKV, tmTh, tmTw;
   {

@@ -28,10 +28,6 @@ def timed(fn, iters=20):
 
 L = _lib.lib()
 res = {"fwd_ms": timed(lambda: ops.attn_fwd(qkv, th, tw, B, heads, h, w))}
-for ns in (300, 500, 700, 900, 1200):      # anti-phase start delay of the SMs' second-slot CTAs
-    L.pk_attn_fwd_stagger(ns)
-    res[f"fwd_stagger{ns}_ms"] = timed(lambda: ops.attn_fwd(qkv, th, tw, B, heads, h, w))
-L.pk_attn_fwd_stagger(0)
 for name, flag in (("bwd_all", 0), ("bwd_no_dq", 4), ("bwd_no_dkv", 8), ("bwd_neither", 12)):
     L.pk_attn_bwd_debug(flag)
     res[name] = timed(lambda: ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w))

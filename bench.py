@@ -430,6 +430,8 @@ def main():
     ap.add_argument("--dp", default="own", choices=["own", "ddp"],
                     help="N > 1: painter_b200.dist_utils.GradSync (bucketed all-reduce of the gradient arena issued "
                          "from backward; default) or stock DistributedDataParallel")
+    ap.add_argument("--hi-prio", action="store_true",
+                    help="N > 1: run the step on a high-priority CUDA stream (NCCL's stream keeps the default priority)")
     ap.add_argument("--sm-reserve", type=int, default=8,
                     help="N > 1, --dp own: SMs left to NCCL while gradient buckets are in flight")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
@@ -463,6 +465,8 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     W_steps = max(args.warmup, 3)
     B = args.batch
+    if args.hi_prio:
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
 
     torch.manual_seed(0)
     if args.workload == "long":

@@ -88,11 +88,11 @@ long long pk_layernorm_bwd_ws_floats(int M, int C); /* fp32 elements of `workspa
 /* pk_layernorm_bwd fused with pk_scale_cast_colsum of its result (the backward of `x + drop_path(attn(norm1(x)))`
  * feeds norm2's input gradient, DropPath-scaled and cast to bf16, straight into the proj GEMMs; models_painter.py:
  * 216-235): also writes dx_bf16 = bf16(rowscale[row / rows_per_group] * dx) and adds its column sums to colsum[C]. */
-int pk_layernorm_bwd_cast(const float* dy, int lddy, const float* x, int ldx, const float* mean, const float* rstd,
+int pk_layernorm_bwd_cast(const void* dy, int dy_is_bf16, int lddy, const float* x, int ldx, const float* mean, const float* rstd,
                           const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta,
                           float* workspace, const float* rowscale, int rows_per_group, void* dx_bf16, float* colsum,
                           int M, int C, void* stream);
-int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* mean, const float* rstd,
+int pk_layernorm_bwd(const void* dy, int dy_is_bf16, int lddy, const float* x, int ldx, const float* mean, const float* rstd,
                      const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta,
                      float* workspace, int M, int C, void* stream);
 

@@ -74,9 +74,11 @@ ln_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ ga
 // its column sums (that GEMM's bias gradient): emitted here instead of re-reading dx in a second kernel; the
 // column sums ride in a third partials block.
 constexpr int LNB_ROWS = 4;
-template <bool FUSE>
+// DYB: dy arrives as bf16 (the dgrad GEMM in front writes bf16 - the rounding point of the reference's autocast Linear
+// backward - which halves both that GEMM's store traffic and this kernel's dy stream).
+template <bool FUSE, bool DYB>
 __global__ void __launch_bounds__(256, FUSE ? 2 : 3)
-ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+ln_bwd_kernel(const void* __restrict__ dy_, int lddy, const float* __restrict__ x, int ldx,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
               float* __restrict__ partials /* [gridDim.x][2C or 3C] */, int M, int C,
@@ -95,7 +97,14 @@ ln_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ 
     for (int u = 0; u < LNB_ROWS; ++u) {
       const int row = min(r0 + u, M - 1);
       xh[u] = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx)[tid];
-      gd[u] = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * lddy)[tid];
+      if constexpr (DYB) {
+        const uint2 q = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy_) +
+                                                       static_cast<size_t>(row) * lddy)[tid];
+        gd[u] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u),
+                            __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xFFFF0000u));
+      } else {
+        gd[u] = reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + static_cast<size_t>(row) * lddy)[tid];
+      }
       if (dres) rv[u] = reinterpret_cast<const float4*>(dres + static_cast<size_t>(row) * C)[tid];
     }
 #pragma unroll
@@ -539,14 +548,18 @@ extern "C" long long pk_layernorm_bwd_ws_floats(int M, int C) {
   return static_cast<long long>(ln_bwd_grid(M)) * 3 * C;
 }
 
-extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* mean,
+extern "C" int pk_layernorm_bwd(const void* dy, int dy_is_bf16, int lddy, const float* x, int ldx, const float* mean,
                                 const float* rstd, const float* gamma, const float* dres, float* dx,
                                 float* dgamma, float* dbeta, float* workspace, int M, int C, void* stream) {
   PK_CHECK(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, "pk_layernorm_bwd: null pointer");
   PK_CHECK(C % 128 == 0 && C <= 1024 && lddy % 4 == 0 && ldx % 4 == 0, "pk_layernorm_bwd: bad C=%d", C);
   const int grid = ln_bwd_grid(M);
-  ln_bwd_kernel<false><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres,
-                                                                            dx, workspace, M, C, nullptr, 0, nullptr);
+  if (dy_is_bf16)
+    ln_bwd_kernel<false, true><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, nullptr, 0, nullptr);
+  else
+    ln_bwd_kernel<false, false><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, nullptr, 0, nullptr);
   PK_LAUNCH_CHECK("pk_layernorm_bwd");
   ln_bwd_reduce_kernel<<<2 * C / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
                                                                                         dbeta, nullptr, C, 2);
@@ -556,7 +569,7 @@ extern "C" int pk_layernorm_bwd(const float* dy, int lddy, const float* x, int l
 
 // pk_layernorm_bwd + pk_scale_cast_colsum of its result in one pass: additionally writes
 // dx_bf16 = bf16(rowscale[row / rows_per_group] * dx) and adds its column sums to colsum[C].
-extern "C" int pk_layernorm_bwd_cast(const float* dy, int lddy, const float* x, int ldx, const float* mean,
+extern "C" int pk_layernorm_bwd_cast(const void* dy, int dy_is_bf16, int lddy, const float* x, int ldx, const float* mean,
                                      const float* rstd, const float* gamma, const float* dres, float* dx,
                                      float* dgamma, float* dbeta, float* workspace, const float* rowscale,
                                      int rows_per_group, void* dx_bf16, float* colsum, int M, int C, void* stream) {
@@ -566,9 +579,14 @@ extern "C" int pk_layernorm_bwd_cast(const float* dy, int lddy, const float* x, 
   if (rowscale) PK_CHECK(rows_per_group > 0, "pk_layernorm_bwd_cast: rows_per_group must be > 0");
   int grid = sm_count() * 2;   // the fused variant keeps 2 blocks per SM resident (<= ln_bwd_grid(M): workspace fits)
   if (grid > (M + LNB_ROWS - 1) / LNB_ROWS) grid = (M + LNB_ROWS - 1) / LNB_ROWS;
-  ln_bwd_kernel<true><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
-      static_cast<__nv_bfloat16*>(dx_bf16));
+  if (dy_is_bf16)
+    ln_bwd_kernel<true, true><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
+        static_cast<__nv_bfloat16*>(dx_bf16));
+  else
+    ln_bwd_kernel<true, false><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
+        static_cast<__nv_bfloat16*>(dx_bf16));
   PK_LAUNCH_CHECK("pk_layernorm_bwd_cast");
   ln_bwd_reduce_kernel<<<3 * C / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
                                                                                         dbeta, colsum, C, 3);

@@ -249,7 +249,9 @@ class BlockFn(torch.autograd.Function):
         dz = ops.gemm(dy, wfc2, trans_b=True, kind=EPI_DGELU, aux=z)
         ops.colsum_bf16(dz, out=dfc1_b)
         dfc1_w = _wgrad(dz, v, out=g_fc1)
-        dv = ops.gemm(dz, wfc1, trans_b=True, kind=EPI_F32)
+        # dgrad outputs that feed a LayerNorm backward are written as bf16 (the reference's autocast Linear backward
+        # rounds there too): half the store traffic of the GEMM epilogue and of the LN-backward's dy stream
+        dv = ops.gemm(dz, wfc1, trans_b=True, kind=EPI_BF16)
         # LN2 backward also emits the attention branch's incoming gradient: bf16(DropPath scale * dx1) + its column sums
         dx1, da = ops.layernorm_bwd(dv, x1, mean2, rstd2, n2w, dn2w, dn2b, dres=dx2, cast=(drop_a, N, dproj_b))
         # ---- attention branch ----
@@ -264,9 +266,11 @@ class BlockFn(torch.autograd.Function):
             dqkv, dTh, dTw = ops.attn_bwd(qkv, ao, dao, lse, th, tw, Bp, heads, h, w, dT_out=(g_th, g_tw))
         ops.colsum_bf16(dqkv, out=dqkv_b)
         dqkv_w = _wgrad(dqkv, u, out=g_qkv)
-        du = ops.gemm(dqkv, wqkv, trans_b=True, kind=EPI_F32)
         if ws > 0:
+            du = ops.gemm(dqkv, wqkv, trans_b=True, kind=EPI_F32)
             du = ops.window_unpartition(du, Bp, h, w, ws)   # gradients at padded tokens are dropped
+        else:
+            du = ops.gemm(dqkv, wqkv, trans_b=True, kind=EPI_BF16)
         below = env.below if act else None
         if below is not None:
             # the block below consumes dx only through bf16(its DropPath scale * dx): emit that (and the fc2 bias
@@ -346,7 +350,7 @@ class DecoderFn(torch.autograd.Function):
         dD = ops.conv3x3_dgrad_unshuffle(dc1, wd, p)          # [M, p*p*64] bf16, token-major
         ddec_b = ops.colsum_bf16(dD, out=G("dec_b"))
         ddec_w = _wgrad(dD, cat, out=G("dec_w"))
-        dcat = ops.gemm(dD, wdec, trans_b=True, kind=EPI_F32)  # [M, 4C] fp32
+        dcat = ops.gemm(dD, wdec, trans_b=True, kind=EPI_BF16)  # [M, 4C] bf16, read by the 4 LayerNorm backwards
         dnw = G("norm_w") if act else torch.zeros(C, dtype=torch.float32, device=dev)
         dnb = G("norm_b") if act else torch.zeros(C, dtype=torch.float32, device=dev)
         dts = []

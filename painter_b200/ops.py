@@ -167,7 +167,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, cast=None)
     """Returns dx fp32 [M, C] (+ dres); accumulates into dgamma / dbeta (fp32, caller-initialised).
     cast = (rowscale or None, rows_per_group, colsum_out[C]): also returns bf16(rowscale * dx) and adds its column
     sums to colsum_out (the fused form of `scale_cast_colsum(layernorm_bwd(...))`)."""
-    _req(dy, torch.float32, "dy")
+    if dy.dtype != torch.bfloat16:
+        _req(dy, torch.float32, "dy")
+    dyb = int(dy.dtype == torch.bfloat16)
     _req(x, torch.float32, "x")
     M, C = x.shape
     assert dy.stride(1) == 1 and x.stride(1) == 1
@@ -180,12 +182,12 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, cast=None)
     if cast is not None:
         rowscale, rpg, cs = cast
         dxb = torch.empty((M, C), dtype=torch.bfloat16, device=x.device)
-        check(L.pk_layernorm_bwd_cast(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd),
+        check(L.pk_layernorm_bwd_cast(_ptr(dy), dyb, dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd),
                                       _ptr(gamma), _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws),
                                       _ptr(rowscale), rpg, _ptr(dxb), _ptr(cs), M, C, _stream()),
               "pk_layernorm_bwd_cast")
         return dx, dxb
-    check(L.pk_layernorm_bwd(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma),
+    check(L.pk_layernorm_bwd(_ptr(dy), dyb, dy.stride(0), _ptr(x), x.stride(0), _ptr(mean), _ptr(rstd), _ptr(gamma),
                              _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), M, C, _stream()),
           "pk_layernorm_bwd")
     return dx

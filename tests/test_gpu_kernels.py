@@ -144,6 +144,20 @@ def test_layernorm_fwd_bwd():
     want = (xr.grad + dres) * rs.repeat_interleave(M // 3)[:, None]
     assert relmax(dx2, xr.grad + dres) < 2e-5 and relmax(dg2, gr.grad) < 1e-4 and relmax(db2, br.grad) < 1e-4
     assert dxb.dtype == torch.bfloat16 and relmax(dxb, want) < 1e-2 and relmax(cs, want.sum(0)) < 1e-4
+    # dy arriving as bf16 (the dgrad GEMM's output dtype), from a column slice of a wider buffer: exact on the
+    # bf16-representable values
+    wide = torch.randn(M, 2 * C, device=DEV).bfloat16()
+    dyb = wide[:, C:]
+    xr.grad = None
+    gr.grad = None
+    br.grad = None
+    F.layer_norm(xr, (C,), gr, br, 1e-6).backward(dyb.float())
+    dg3, db3 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dx3 = ops.layernorm_bwd(dyb, x, mean, rstd, g, dg3, db3, dres=dres)
+    assert relmax(dx3, xr.grad + dres) < 2e-5 and relmax(dg3, gr.grad) < 1e-4 and relmax(db3, br.grad) < 1e-4
+    dg4, db4, cs4 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dx4, _ = ops.layernorm_bwd(dyb, x, mean, rstd, g, dg4, db4, dres=dres, cast=(rs, M // 3, cs4))
+    assert relmax(dx4, xr.grad + dres) < 2e-5 and relmax(dg4, gr.grad) < 1e-4
 
 
 def test_patch_embed_lowering_and_token_assembly():

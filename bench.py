@@ -430,9 +430,12 @@ def main():
     ap.add_argument("--dp", default="own", choices=["own", "ddp"],
                     help="N > 1: painter_b200.dist_utils.GradSync (bucketed all-reduce of the gradient arena issued "
                          "from backward; default) or stock DistributedDataParallel")
-    ap.add_argument("--hi-prio", action="store_true",
-                    help="N > 1: run the step on a high-priority CUDA stream (NCCL's stream keeps the default priority)")
-    ap.add_argument("--sm-reserve", type=int, default=8,
+    ap.add_argument("--no-hi-prio", action="store_true",
+                    help="N > 1: do NOT run the step on a high-priority CUDA stream (default: compute outranks NCCL's "
+                         "stream, so a pending GEMM CTA gets a freed SM before a pending NCCL CTA does)")
+    ap.add_argument("--bg-ctas", type=int, default=4,
+                    help="N > 1, --dp own: CTA limit of the communicator used for all but the last gradient buckets")
+    ap.add_argument("--sm-reserve", type=int, default=4,
                     help="N > 1, --dp own: SMs left to NCCL while gradient buckets are in flight")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--precision", default="both", choices=["bf16", "fp32", "both"],
@@ -465,7 +468,7 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     W_steps = max(args.warmup, 3)
     B = args.batch
-    if args.hi_prio:
+    if world > 1 and not args.no_hi_prio:
         torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
 
     torch.manual_seed(0)
@@ -487,7 +490,7 @@ def main():
     if world > 1:
         if args.dp == "own":
             gsync = dist_utils.GradSync(model, bucket_mb=args.bucket_mb if args.bucket_mb > 25 else 200,
-                                        sm_reserve=args.sm_reserve)
+                                        sm_reserve=args.sm_reserve, bg_ctas=args.bg_ctas)
         else:
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                             bucket_cap_mb=args.bucket_mb)

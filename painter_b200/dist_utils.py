@@ -41,12 +41,24 @@ class GradSync:
     Semantics = DDP: parameters are broadcast from rank 0 at construction, gradients are averaged over ranks
     every backward (also with gradient accumulation, like engine_train.py which never uses no_sync())."""
 
-    def __init__(self, model, process_group=None, bucket_mb=200, sm_reserve=0, broadcast=True):
+    def __init__(self, model, process_group=None, bucket_mb=200, sm_reserve=0, broadcast=True, bg_ctas=0,
+                 tail_mb=120):
+        """bg_ctas > 0 (NCCL only): buckets whose all-reduce has the rest of backward to hide behind run on a second
+        communicator limited to `bg_ctas` CTAs (NCCL's default of up to 32 CTAs takes that many SMs away from the
+        persistent GEMM grids for the duration of every bucket); the last `tail_mb` MB of gradients - whose latency
+        is exposed at the end of backward - keep the full-width default communicator."""
         from .arena import get_arena
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.backend = dist.get_backend(process_group)
         self.sm_reserve = int(sm_reserve)
+        self.bg_group = None
+        if bg_ctas > 0 and self.backend == "nccl" and self.world > 1:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(bg_ctas)
+            opts.config.min_ctas = 1
+            self.bg_group = dist.new_group(backend="nccl", pg_options=opts)
+        self.tail_floats = int(tail_mb * (1 << 20) / 4)
         arena = get_arena(model)
         arena.sync = self
         self.arena = arena
@@ -93,7 +105,10 @@ class GradSync:
             if self.world > 1 and not os.environ.get("PK_GRADSYNC_SKIP"):   # (diagnostic: everything but the wire)
                 t = arena.cur[a:b]
                 if self.backend == "nccl":
-                    w = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                    g = self.group
+                    if self.bg_group is not None and b <= arena.total - self.tail_floats:
+                        g = self.bg_group
+                    w = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=g, async_op=True)
                     self._works.append((w, None))
                 else:
                     w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)

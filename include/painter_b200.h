@@ -145,17 +145,13 @@ int pk_ensemble_resid(const float* a, const float* z, float* out, int G, int P, 
  * bwd: dqkv bf16 like qkv; dTh [2h-1,64], dTw [2w-1,64] fp32, added to (zero-initialise);
  *      scratch: delta [B*heads*N], relh_g [B*heads*N*h], relw_g [B*heads*N*w], dt_ws
  *      [pk_attn_bwd_ws_floats(B, heads, h, w)] fp32 (per-CTA partial table gradients, reduced by a
- *      second kernel instead of same-address atomics); ps_ws: nullable bf16 scratch of
- *      pk_attn_bwd_ps_elems(B, heads, h, w) elements - when given (and that count is non-zero) the dQ kernel streams its
- *      P / dS tiles there (TMA stores) and dK / dV are two plain tensor-core GEMMs over them instead of a second
- *      recomputation of the scores and the softmax.                                                         */
+ *      second kernel instead of same-address atomics).                                                     */
 int pk_relpos_table_bf16(const float* table, void* out_bf16, int L, int Lpad, void* stream);
 int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void* out, float* lse, int B, int heads, int h,
                 int w, int th_pad, int tw_pad, void* stream);
 int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse, const void* th, const void* tw,
                 void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g, float* relw_g, float* dt_ws,
-                void* ps_ws, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream);
-long long pk_attn_bwd_ps_elems(int B, int heads, int h, int w);
+                int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream);
 long long pk_attn_bwd_ws_floats(int B, int heads, int h, int w);
 
 /* ------------------------------------------------------------------------------------------------

@@ -28,8 +28,6 @@ namespace pk {
 constexpr int AB_BM = 128;
 constexpr int AB_KT = 112;
 constexpr int AB_THREADS = 352;   // 8 softmax warps + TMA warp + two tcgen05 issuing warps (scores | accumulations)
-constexpr int AA_THREADS = 384;   // kernel A: + one warp that streams the P / dS tiles to global memory (for kernel B2)
-constexpr int AB_TP = 128;        // column pitch of one key tile in the P / dS scratch (112 valid + 16 padding)
 constexpr int AB_SMX = 256;       // softmax threads
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
@@ -45,8 +43,7 @@ constexpr uint32_t A_SQ = 0;                    // Q tile 128 x 128 B
 constexpr uint32_t A_SDO = 16384;               // dO tile
 constexpr uint32_t A_SDS = 32768;               // 2 x dS tile (2 K-blocks each, double-buffered); T_h staged in
                                                 // buffer 0 during the prologue; epilogue: G^ buffer (<= 4 K-blocks)
-constexpr uint32_t A_SP = A_SDS + 65536;        // P tile (2 K-blocks, single buffer): staged for the TMA store to global
-constexpr uint32_t A_SKV = A_SP + 32768;        // kv_stages (2 or 3) x (K 14336 | V 14336)
+constexpr uint32_t A_SKV = A_SDS + 65536;       // kv_stages (2 or 3) x (K 14336 | V 14336)
 constexpr uint32_t A_STH = A_SKV;               // epilogue: T_h reload (<= 28 KiB) over stage 0
 constexpr uint32_t A_STW = A_SKV + 28672;       // epilogue: T_w reload (<= 14 KiB) over stage 1
 // rel_h rows fp32 [128][h+1] follow the K/V stages (Gh' sums overwrite them in place): A_SKV + kv_stages * 28672
@@ -70,7 +67,6 @@ struct AttnBwdArgs {
   int debug;                 // measurement aids: bit 1 trace the last (b, head) CTA instead of the first,
                              // bit 2 skip kernel A, bit 3 skip kernel B (scripts/time_attn_parts.py)
   int kv_stages;             // kernel A: K/V ring depth (3 normally; 2 when shared memory is short)
-  int store_ps;              // kernel A: stream P and dS tiles to the scratch for attn_bwd_dkv2_kernel
 };
 
 // debug timeline: `ab_tr` (one predicate register per thread, set at kernel entry) selects the traced CTA, so a
@@ -86,11 +82,10 @@ struct AttnBwdArgs {
   } while (0)
 
 template <int W>
-__global__ void __launch_bounds__(AA_THREADS, 1)
+__global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmTh,
-                   const __grid_constant__ CUtensorMap tmTw, const __grid_constant__ CUtensorMap tmPst,
-                   const __grid_constant__ CUtensorMap tmdSst, const AttnBwdArgs a) {
+                   const __grid_constant__ CUtensorMap tmTw, const AttnBwdArgs a) {
   constexpr int R = AB_KT / W;
   AB_TRACE_INIT();
   extern __shared__ uint8_t smem_raw[];
@@ -98,7 +93,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t base = (raw_base + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw_base);
 
-  const uint32_t sQ = base + A_SQ, sdO = base + A_SDO, sdS = base + A_SDS, sKV = base + A_SKV, sPt = base + A_SP;
+  const uint32_t sQ = base + A_SQ, sdO = base + A_SDO, sdS = base + A_SDS, sKV = base + A_SKV;
   const int KS = a.kv_stages;
   const uint32_t srelh_off = A_SKV + static_cast<uint32_t>(KS) * 28672u;
   float* relh_gen = reinterpret_cast<float*>(gen + srelh_off);
@@ -107,12 +102,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                  bar_p1 = bar0 + 72, bar_df = bar0 + 80 /*2*/,
                  bar_s = bar0 + 104 /*2*/, bar_p0 = bar0 + 120, bar_g = bar0 + 128,
                  bar_gr = bar0 + 136, bar_e = bar0 + 144, bar_er = bar0 + 152, bar_t = bar0 + 160,
-                 bar_gw = bar0 + 168,  // G_w retired (single completion; bar_g completes twice and would alias)
-                 bar_pf = bar0 + 176;  // P staging tile drained by the store warp
-  const uint32_t holder = bar0 + 184;
+                 bar_gw = bar0 + 168;  // G_w retired (single completion; bar_g completes twice and would alias)
+  const uint32_t holder = bar0 + 176;
   volatile uint32_t* holder_gen =
-      reinterpret_cast<volatile uint32_t*>(gen + srelh_off + a.relh_bytes + 184);
-  const int dfc = a.store_ps ? 2 : 1;   // dS buffer free = dQ MMAs retired (+ its TMA store has read it)
+      reinterpret_cast<volatile uint32_t*>(gen + srelh_off + a.relh_bytes + 176);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AB_BM;
@@ -141,9 +134,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_p0, AB_SMX / 32);
     mbar_init(bar_p1, AB_SMX / 32);
-    mbar_init(bar_df, dfc);
-    mbar_init(bar_df + 8, dfc);
-    mbar_init(bar_pf, 1);
+    mbar_init(bar_df, 1);
+    mbar_init(bar_df + 8, 1);
     mbar_init(bar_g, 1);
     mbar_init(bar_gr, AB_SMX);
     mbar_init(bar_e, 1);
@@ -299,30 +291,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       __syncwarp();
     }
-  } else if (warp == 11) {
-    // ------------------------------ store warp: P(j), dS(j) tiles -> global scratch ------------------------------
-    // The tiles the softmax warps hand to the dQ MMAs (bf16, K-major 128B-swizzled, two K-blocks of 64 + 48 keys) are
-    // exactly the image a TMA store with the same swizzle expects: kernel B2 (dK, dV) reads them back instead of
-    // recomputing S, dP and the softmax.  Column pitch of a key tile in the scratch is AB_TP = 128, so both K-blocks are
-    // stored as full 64-column boxes (the 16 padding columns receive stale data that nobody reads as a valid key).
-    if (a.store_ps && lane == 0) {
-      const int bh = b * a.heads + head;
-      for (int j = 0; j < num_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(st ? bar_p1 : bar_p0, (j >> 1) & 1);
-        const uint32_t src_ds = sdS + st * 32768;
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          tma_store_3d(&tmdSst, src_ds + kb * 16384, j * AB_TP + kb * 64, q0, bh);
-          tma_store_3d(&tmPst, sPt + kb * 16384, j * AB_TP + kb * 64, q0, bh);
-        }
-        tma_store_commit();
-        tma_store_wait_read0();
-        mbar_arrive(bar_df + 8 * st);
-        mbar_arrive(bar_pf);
-      }
-      tma_store_wait_all();   // global writes complete before the CTA exits
-    }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
     // 8 warps: warps 0..3 own key columns [0,56) of every tile, warps 4..7 columns [56,112) (warp 8 = TMA, warps 9 / 10 =
@@ -452,7 +420,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t tS_h = tS + (j & 1) * 224 + lane_addr + cbase, tdP_h = tS_h + 112;
       const uint32_t sdS_j = sdS + (j & 1) * 32768;
       if (j >= 2) mbar_wait(bar_df + 8 * (j & 1), ((j >> 1) - 1) & 1);  // dQ(j-2) has drained this dS buffer
-      if (a.store_ps && j >= 1) mbar_wait(bar_pf, (j - 1) & 1);          // P(j-1) has left the staging tile
       // 56 columns per thread as 7 chunks of 8, software-pipelined: the TMEM loads of chunk ci + 1 are in flight
       // while chunk ci is processed (two softmax warps per scheduler cannot hide a tcgen05.ld round trip per chunk)
       uint32_t v[2][8], w[2][8];
@@ -466,40 +433,34 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_ld_x8(tS_h + c0 + 8, v[(ci + 1) & 1]);
           tmem_ld_x8(tdP_h + c0 + 8, w[(ci + 1) & 1]);
         }
-        uint32_t dsb[4], pb[4];
+        uint32_t dsb[4];
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
           const int kc = c0 + c;
           const uint32_t v0 = v[ci & 1][c], v1 = v[ci & 1][c + 1], w0 = w[ci & 1][c], w1 = w[ci & 1][c + 1];
-          float d0, d1, p0, p1;
+          float d0, d1;
           if constexpr (PK2) {
             const f32x2 t2 = fma_f2(pack_u2(v0, v1), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2]));
             float t0, t1;
             unpack_f2(t2, t0, t1);
-            p0 = fast_exp2(t0);
-            p1 = fast_exp2(t1);
-            const f32x2 d2 = mul_f2(pack_f2(p0, p1), add_f2(pack_u2(w0, w1), nd2));
+            const f32x2 d2 = mul_f2(pack_f2(fast_exp2(t0), fast_exp2(t1)), add_f2(pack_u2(w0, w1), nd2));
             gh2[kc / W] = add_f2(gh2[kc / W], d2);
             gw2[(kc % W) / 2] = add_f2(gw2[(kc % W) / 2], d2);
             unpack_f2(d2, d0, d1);
           } else {
             const int k1 = kc + 1;
-            p0 = fast_exp2(fmaf(__uint_as_float(v0), sc, hb[kc / W] + relw[kc % W]));
-            p1 = fast_exp2(fmaf(__uint_as_float(v1), sc, hb[k1 / W] + relw[k1 % W]));
-            d0 = p0 * (__uint_as_float(w0) - delta);
-            d1 = p1 * (__uint_as_float(w1) - delta);
+            d0 = fast_exp2(fmaf(__uint_as_float(v0), sc, hb[kc / W] + relw[kc % W])) * (__uint_as_float(w0) - delta);
+            d1 = fast_exp2(fmaf(__uint_as_float(v1), sc, hb[k1 / W] + relw[k1 % W])) * (__uint_as_float(w1) - delta);
             gh[kc / W] += d0;
             gh[k1 / W] += d1;
             gw[kc % W] += d0;
             gw[k1 % W] += d1;
           }
           dsb[c / 2] = pack_bf16x2(d0, d1);
-          pb[c / 2] = pack_bf16x2(p0, p1);
         }
         const int g8 = (cbase + c0) >> 3;  // 8-column group inside the 112-wide tile
-        const uint32_t toff = (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4);
-        st_shared_v4(sdS_j + toff, dsb[0], dsb[1], dsb[2], dsb[3]);
-        if (a.store_ps) st_shared_v4(sPt + toff, pb[0], pb[1], pb[2], pb[3]);
+        st_shared_v4(sdS_j + (g8 >> 3) * 16384 + row * 128 + (((g8 & 7) ^ (row & 7)) << 4), dsb[0], dsb[1], dsb[2],
+                     dsb[3]);
       }
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
@@ -528,10 +489,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // (dS is stored unscaled, so the accumulator holds 8 * dQ_bias + dS.K; the final read-out multiplies by 1/8)
     mbar_wait(bar_e, 0);
     tc_fence_after();
-    // the Ĝ operands below overwrite the dS buffers: their last readers (dQ MMAs and, when the tiles are streamed to
-    // global memory, the TMA stores) must have drained them
-    if (num_tiles > 0) mbar_wait(bar_df, ((num_tiles - 1) >> 1) & 1);
-    if (num_tiles > 1) mbar_wait(bar_df + 8, ((num_tiles - 2) >> 1) & 1);
     for (int c0 = half * 8; c0 < a.th_pad; c0 += 16) {
       float g[8];
 #pragma unroll
@@ -983,131 +940,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
-// ================================================================================================
-// Kernel B2: dK, dV from the P / dS tiles kernel A streamed to global memory - two plain GEMMs per key tile,
-//   dK[keys, d] = 0.125 * sum_q dS[q, keys]^T Q[q, d],   dV[keys, d] = sum_q P[q, keys]^T dO[q, d],
-// with no score recomputation, no softmax and no exp2: the kernel is a TMA -> tcgen05 pipe bounded by the HBM / L2
-// stream of the two bf16 tiles (2 x 32 KB per 128 queries).  CTA = one key tile (128-column pitch in the scratch,
-// 112 valid keys); 6 warps: 0..3 epilogue (accumulator row = key), 4 TMA producer, 5 MMA issuer.
-// ================================================================================================
-constexpr int B2_THREADS = 192;
-constexpr uint32_t B2_STAGE = 98304;        // P 32768 | dS 32768 | Q 16384 | dO 16384
-constexpr int B2_STAGES = 2;
-constexpr uint32_t B2_BARS = B2_STAGE * B2_STAGES;
-
-__global__ void __launch_bounds__(B2_THREADS, 1)
-attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                     const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmdS,
-                     const AttnBwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_base = smem_u32(smem_raw);
-  const uint32_t base = (raw_base + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - raw_base);
-  const uint32_t bar0 = base + B2_BARS;
-  const uint32_t bar_f = bar0, bar_e = bar0 + 8 * B2_STAGES, bar_o = bar0 + 16 * B2_STAGES;
-  const uint32_t holder = bar_o + 8;
-  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + B2_BARS + 16 * B2_STAGES + 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-  const int C = a.heads * 64;
-  const int bh = b * a.heads + head;
-  const int num_q = (a.N + AB_BM - 1) / AB_BM;
-
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmdO);
-    tma_prefetch_desc(&tmP);
-    tma_prefetch_desc(&tmdS);
-    for (int q = 0; q < B2_STAGES; ++q) {
-      mbar_init(bar_f + 8 * q, 1);
-      mbar_init(bar_e + 8 * q, 1);
-    }
-    mbar_init(bar_o, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(holder, 128);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *holder_gen;
-  const uint32_t tdK = tmem, tdV = tmem + 64;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      for (int i = 0; i < num_q; ++i) {
-        const int st = i % B2_STAGES;
-        if (i >= B2_STAGES) mbar_wait(bar_e + 8 * st, ((i / B2_STAGES) - 1) & 1);
-        const uint32_t s0 = base + st * B2_STAGE;
-        mbar_expect_tx(bar_f + 8 * st, B2_STAGE);
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          tma_load_3d(s0 + kb * 16384, &tmP, bar_f + 8 * st, jt * AB_TP + kb * 64, i * AB_BM, bh);
-          tma_load_3d(s0 + 32768 + kb * 16384, &tmdS, bar_f + 8 * st, jt * AB_TP + kb * 64, i * AB_BM, bh);
-        }
-        tma_load_3d(s0 + 65536, &tmQ, bar_f + 8 * st, head * 64, i * AB_BM, b);
-        tma_load_3d(s0 + 81920, &tmdO, bar_f + 8 * st, head * 64, i * AB_BM, b);
-      }
-    }
-  } else if (warp == 5) {
-    const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
-    for (int i = 0; i < num_q; ++i) {
-      const int st = i % B2_STAGES;
-      mbar_wait(bar_f + 8 * st, (i / B2_STAGES) & 1);
-      tc_fence_after();
-      const uint32_t s0 = base + st * B2_STAGE;
-      const uint64_t dP0 = make_sdesc(s0, 16384, 1024), ddS0 = make_sdesc(s0 + 32768, 16384, 1024);
-      const uint64_t dQ0 = make_sdesc(s0 + 65536, 16, 1024), ddO0 = make_sdesc(s0 + 81920, 16, 1024);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tdK, sdesc_add(ddS0, kk * 2048), sdesc_add(dQ0, kk * 2048), idesc_tt, (i | kk) != 0);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tdV, sdesc_add(dP0, kk * 2048), sdesc_add(ddO0, kk * 2048), idesc_tt, (i | kk) != 0);
-        umma_commit(bar_e + 8 * st);
-        if (i == num_q - 1) umma_commit(bar_o);
-      }
-      __syncwarp();
-    }
-  } else {
-    // epilogue: accumulator row = key jt*112 + row (rows >= 112 belong to the padding columns of the scratch)
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    const int u = jt * AB_KT + row;
-    const bool kvalid = row < AB_KT && u < a.N;
-    __nv_bfloat16* dstk = a.dqkv + (static_cast<size_t>(b) * a.N + (kvalid ? u : 0)) * (3 * C) + C + head * 64;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t tacc = which == 0 ? tdK : tdV;
-      const float osc = which == 0 ? 0.125f : 1.0f;     // dS is stored unscaled
-      __nv_bfloat16* dst = dstk + which * C;
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t o[16];
-        tmem_ld_x16(tacc + lane_addr + c0, o);
-        tmem_wait_ld();
-        if (kvalid) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint4 uu;
-            uu.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * osc, __uint_as_float(o[q * 8 + 1]) * osc);
-            uu.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * osc, __uint_as_float(o[q * 8 + 3]) * osc);
-            uu.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * osc, __uint_as_float(o[q * 8 + 5]) * osc);
-            uu.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * osc, __uint_as_float(o[q * 8 + 7]) * osc);
-            *reinterpret_cast<uint4*>(dst + c0 + q * 8) = uu;
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 5) tmem_dealloc(tmem, 128);
-}
-
 }  // namespace pk
 
 using namespace pk;
@@ -1187,24 +1019,10 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __re
   }
 }
 
-// bf16 elements of the P / dS scratch (two [B*heads, N, tiles*128] arrays) the streamed backward needs, or 0 when the
-// geometry does not fit kernel A's shared memory next to the P staging tile (the recomputing kernel B is used then)
-extern "C" long long pk_attn_bwd_ps_elems(int B, int heads, int h, int w) {
-  if (w <= 0 || AB_KT % w != 0) return 0;
-  int relh_bytes = 128 * (h + 1) * 4;
-  if (relh_bytes < 20480) relh_bytes = 20480;
-  if (relh_bytes < 128 * (w + 1) * 4) relh_bytes = 128 * (w + 1) * 4;
-  relh_bytes = (relh_bytes + 15) & ~15;
-  if (1024 + A_SKV + 2 * 28672 + static_cast<size_t>(relh_bytes) + 192 > 227 * 1024) return 0;
-  const int R = AB_KT / w;
-  const long long tiles = (h + R - 1) / R;
-  return 2ll * B * heads * (static_cast<long long>(h) * w) * tiles * AB_TP;
-}
-
 extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
                            const void* tw, void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g,
-                           float* relw_g, float* dt_ws, void* ps_ws, int B, int heads, int h, int w, int th_pad,
-                           int tw_pad, void* stream) {
+                           float* relw_g, float* dt_ws, int B, int heads, int h, int w, int th_pad, int tw_pad,
+                           void* stream) {
   PK_CHECK(qkv && O && dO && lse && th && tw && dqkv && dTh && dTw && delta && relh_g && relw_g && dt_ws,
            "pk_attn_bwd: null pointer");
   PK_CHECK(th_pad % 16 == 0 && tw_pad % 16 == 0 && th_pad >= 2 * h - 1 && tw_pad >= 2 * w - 1 &&
@@ -1226,11 +1044,8 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   a.dt_ws = dt_ws;
   a.trace = g_attnb_trace;
   a.debug = g_attnb_debug;
-  // streamed backward (kernel A writes P / dS tiles, kernel B2 consumes them) unless the scratch was not provided,
-  // the geometry does not fit, or the recomputing kernel B is forced (debug bit 16)
-  a.store_ps = (ps_ws != nullptr && pk_attn_bwd_ps_elems(B, heads, h, w) > 0 && !(g_attnb_debug & 16)) ? 1 : 0;
 
-  CUtensorMap tmQ, tmKV, tmdO, tmTh, tmTw, tmPst, tmdSst;
+  CUtensorMap tmQ, tmKV, tmdO, tmTh, tmTw;
   {
     uint64_t dims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
     uint64_t strides[2] = {static_cast<uint64_t>(3 * C) * 2, static_cast<uint64_t>(N) * 3 * C * 2};
@@ -1252,23 +1067,6 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   a.kv_stages = (1024 + A_SKV + 3 * 28672 + static_cast<size_t>(relh_bytes) + 192 <= 227 * 1024) ? 3 : 2;
   const size_t smemA = 1024 + A_SKV + static_cast<size_t>(a.kv_stages) * 28672 + relh_bytes + 192;
   const size_t smemB = 1024 + B_BARS + 192;
-  const size_t smemB2 = 1024 + B2_BARS + 128;
-  {
-    const int R0 = AB_KT / w;
-    const uint64_t tiles = static_cast<uint64_t>((h + R0 - 1) / R0);
-    if (a.store_ps) {
-      const uint64_t TPw = tiles * AB_TP, BH = static_cast<uint64_t>(B) * heads;
-      uint64_t dimp[3] = {TPw, static_cast<uint64_t>(N), BH};
-      uint64_t strp[2] = {TPw * 2, static_cast<uint64_t>(N) * TPw * 2};
-      uint32_t boxp[3] = {64, AB_BM, 1};
-      __nv_bfloat16* pbase = static_cast<__nv_bfloat16*>(ps_ws);
-      if (!make_tmap_bf16(&tmPst, pbase, 3, dimp, strp, boxp)) return 3;
-      if (!make_tmap_bf16(&tmdSst, pbase + BH * N * TPw, 3, dimp, strp, boxp)) return 3;
-    } else {
-      tmPst = tmQ;
-      tmdSst = tmQ;
-    }
-  }
   PK_CHECK(smemA <= 227 * 1024, "pk_attn_bwd: h=%d needs %zu B of shared memory", h, smemA);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
@@ -1286,16 +1084,11 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
     if (!attr) {                                                                                               \
       cudaFuncSetAttribute(attn_bwd_dq_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
       cudaFuncSetAttribute(attn_bwd_dkv_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  \
-      cudaFuncSetAttribute(attn_bwd_dkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
       attr = true;                                                                                             \
     }                                                                                                          \
-    if (!(a.debug & 4))                                                                                        \
-      attn_bwd_dq_kernel<WW><<<gridA, AA_THREADS, smemA, st>>>(tmQ, tmKV, tmdO, tmTh, tmTw, tmPst, tmdSst, a);  \
+    if (!(a.debug & 4)) attn_bwd_dq_kernel<WW><<<gridA, AB_THREADS, smemA, st>>>(tmQ, tmKV, tmdO, tmTh, tmTw, a); \
     PK_LAUNCH_CHECK("pk_attn_bwd(dq)");                                                                        \
-    if (!(a.debug & 8)) {                                                                                      \
-      if (a.store_ps) attn_bwd_dkv2_kernel<<<gridB, B2_THREADS, smemB2, st>>>(tmQ, tmdO, tmPst, tmdSst, a);     \
-      else attn_bwd_dkv_kernel<WW><<<gridB, AB_THREADS, smemB, st>>>(tmQ, tmKV, tmdO, a);                       \
-    }                                                                                                          \
+    if (!(a.debug & 8)) attn_bwd_dkv_kernel<WW><<<gridB, AB_THREADS, smemB, st>>>(tmQ, tmKV, tmdO, a);          \
     PK_LAUNCH_CHECK("pk_attn_bwd(dkv)");                                                                       \
   } break;
   switch (w) {

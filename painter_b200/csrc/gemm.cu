@@ -540,11 +540,16 @@ extern "C" int pk_decoder_head_fwd(const void* g_nhwc, const void* wmat, const f
   PK_CHECK(g_nhwc && wmat && head_params && tgts && mask && valid && c1_out && patch_out && num,
            "pk_decoder_head_fwd: null pointer");
   PK_CHECK(H % p == 0 && W % p == 0 && maskB >= 1, "pk_decoder_head_fwd: bad geometry");
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_head, head_params, 387 * sizeof(float), 0,
+  // the head parameters ride in constant memory (operands of the epilogue's FFMAs): every call takes the next of
+  // HEAD_SLOTS copies, uploaded on the call's stream just ahead of its kernel
+  static std::atomic<unsigned> next_slot{0};
+  const int slot = static_cast<int>(next_slot.fetch_add(1, std::memory_order_relaxed) % HEAD_SLOTS);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_head_all, head_params, 387 * sizeof(float), slot * 392 * sizeof(float),
                                           cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
   PK_CHECK(e == cudaSuccess, "pk_decoder_head_fwd: constant upload: %s", cudaGetErrorString(e));
   GemmArgs g;
   memset(&g, 0, sizeof(g));
+  g.head.slot = slot;
   g.epi.kind = EPI_HEAD;
   g.epi.alpha = 1.0f;
   g.head.tgts = tgts; g.head.mask = mask; g.head.valid = valid; g.head.maskB = maskB;

@@ -36,6 +36,7 @@ struct HeadArgs {
   float* patch_out;         // [B, N, p*p*3]
   float* num;               // [B] atomics: sum smoothl1 * mask * valid
   int maskB, p, loss_kind;
+  int slot;                 // which copy of the head parameters in constant memory this launch reads
 };
 
 // operand ring depth that fits beside the 8 epilogue staging tiles
@@ -124,7 +125,10 @@ __host__ __device__ __forceinline__ void gemm_tile_coords(const GemmArgs& g, int
 
 // decoder-head parameters, refreshed per call by async D2D copies:
 // [0,64) conv bias | [64,128) LN2D gamma | [128,192) LN2D beta | [192,384) 1x1 weight [3][64] | [384,387) 1x1 bias
-static __constant__ float c_head[392];   // one copy per translation unit; only gemm.cu (EPI_HEAD) writes and reads it
+// HEAD_SLOTS copies, handed out round-robin per call (HeadArgs::slot): launches on different streams - or queued
+// back to back with different parameters - never share a copy unless more than HEAD_SLOTS head launches are in flight
+constexpr int HEAD_SLOTS = 8;
+static __constant__ float c_head_all[HEAD_SLOTS][392];   // only gemm.cu (EPI_HEAD) writes and reads it
 
 __device__ __forceinline__ float smooth_l1(float d, int kind) {
   const float ad = fabsf(d);
@@ -138,6 +142,7 @@ __device__ __forceinline__ float smooth_l1(float d, int kind) {
 // vitdet_utils.py:204-209 + forward_loss :433-462 + patchify :355-368.
 __device__ __forceinline__ void head_epilogue_row(const GemmArgs& g, int b, int y, int x, float (&c)[64]) {
   const HeadArgs& hd = g.head;
+  const float* c_head = c_head_all[hd.slot];
   const int H = g.conv.H, W = g.conv.W, p = hd.p;
   // conv bias, round to bf16 (the conv output is what backward re-reads), store NHWC
   float mean = 0.f;

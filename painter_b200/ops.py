@@ -137,13 +137,10 @@ def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None, dT
     relw_g = torch.empty((B * heads * N * w,), dtype=torch.float32, device=dev)
     L = lib()
     L.pk_attn_bwd_ws_floats.restype = ctypes.c_longlong
-    L.pk_attn_bwd_ps_elems.restype = ctypes.c_longlong
     dt_ws = torch.empty((int(L.pk_attn_bwd_ws_floats(B, heads, h, w)),), dtype=torch.float32, device=dev)
-    n_ps = int(L.pk_attn_bwd_ps_elems(B, heads, h, w))      # P / dS tile scratch of the streamed backward (0: n/a)
-    ps = torch.empty((n_ps,), dtype=torch.bfloat16, device=dev) if n_ps > 0 else None
     check(lib().pk_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(th), _ptr(tw), _ptr(dqkv),
-                            _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), _ptr(dt_ws), _ptr(ps),
-                            B, heads, h, w, th.shape[0], tw.shape[0], _stream()), "pk_attn_bwd")
+                            _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), _ptr(dt_ws), B, heads, h, w,
+                            th.shape[0], tw.shape[0], _stream()), "pk_attn_bwd")
     return dqkv, dTh, dTw
 
 

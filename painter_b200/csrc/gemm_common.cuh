@@ -347,11 +347,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
       const int row = row0 + it * 4 + rsub;
       if (row >= M) continue;
       float* d = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldc + cc;
-      if (KIND == PK_EPI_F32 && e.accumulate == 2) {  // split-K partials
-        atomicAdd(d + 0, xs[it].x);
-        atomicAdd(d + 1, xs[it].y);
-        atomicAdd(d + 2, xs[it].z);
-        atomicAdd(d + 3, xs[it].w);
+      if (KIND == PK_EPI_F32 && e.accumulate == 2) {  // split-K / stream-K partials
+        // one 16-byte vector reduction per thread instead of four scalar ones: the partial tiles of a weight-gradient
+        // GEMM are 32 K fp32 per CTA, and at ~1.3 cycles per scalar lane the atomics were ~40 % of those kernels
+        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(xs[it].x),
+                     "f"(xs[it].y), "f"(xs[it].z), "f"(xs[it].w)
+                     : "memory");
       } else {
         *reinterpret_cast<float4*>(d) = xs[it];
       }

@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpainter_b200.so")
+LIB_PATH = os.environ.get("PK_LIB") or os.path.join(_HERE, "libpainter_b200.so")   # PK_LIB: a tuning build
 
 _lib = None
 

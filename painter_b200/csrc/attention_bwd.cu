@@ -443,7 +443,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const f32x2 t2 = fma_f2(pack_u2(v0, v1), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2]));
             float t0, t1;
             unpack_f2(t2, t0, t1);
-            const f32x2 d2 = mul_f2(pack_f2(fast_exp2(t0), fast_exp2(t1)), add_f2(pack_u2(w0, w1), nd2));
+            float p0, p1;
+            exp2_pair(c >> 1, t0, t1, p0, p1);
+            const f32x2 d2 = mul_f2(pack_f2(p0, p1), add_f2(pack_u2(w0, w1), nd2));
             gh2[kc / W] = add_f2(gh2[kc / W], d2);
             gw2[(kc % W) / 2] = add_f2(gw2[(kc % W) / 2], d2);
             unpack_f2(d2, d0, d1);
@@ -524,30 +526,36 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     {
-      // combine the two halves' column sums through smem (the rel_h / Gh' rows are dead by now)
-      float* xch = relh_gen + static_cast<size_t>(row) * (W + 1);
+      // Total column sums Gw'[row][j] (both column halves) through smem (the rel_h / Gh' rows are dead by now), then
+      // the Toeplitz re-indexed operand row Gw^[row][t] = 8 * Gw'[row][j_r + W-1 - t] is assembled from them in
+      // registers and written as whole 16-byte chunks, the two halves sharing the chunks.  (Round 1 scattered 2-byte
+      // stores instead: 32 rows of a warp hit one bank - a 32-way conflict per store, ~3.5 k cycles per CTA.)
+      float* xch = relh_gen + static_cast<size_t>(row) * (W + 1);     // row stride W+1 floats: conflict-free
       if (half == 1) {
 #pragma unroll
         for (int j = 0; j < W; ++j) xch[j] = gw[j];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(AB_SMX) : "memory");
       if (half == 0) {
-        // zero this row of the first two K-blocks, then scatter gw[j] to column t = j_r + W-1 - j
-        const uint32_t rb0 = sdS + row * 128, rb1 = sdS + 16384 + row * 128;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          st_shared_v4(rb0 + (q << 4), 0u, 0u, 0u, 0u);
-          st_shared_v4(rb1 + (q << 4), 0u, 0u, 0u, 0u);
-        }
+        for (int j = 0; j < W; ++j) xch[j] += gw[j];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(AB_SMX) : "memory");
+      for (int c0 = half * 8; c0 < a.tw_pad; c0 += 16) {
+        float g[8];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-          const int tt = j_r + (W - 1) - j;
-          const uint32_t addr = sdS + (tt >> 6) * 16384 + row * 128 + ((((tt & 63) >> 3) ^ (row & 7)) << 4) +
-                                (tt & 7) * 2;
-          const __nv_bfloat16 bv = __float2bfloat16_rn((gw[j] + xch[j]) * 8.0f);
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&bv))
-                       : "memory");
+        for (int c = 0; c < 8; ++c) {
+          const int j = j_r + (W - 1) - (c0 + c);
+          g[c] = (j >= 0 && j < W) ? xch[j] * 8.0f : 0.f;
         }
+        const uint32_t addr = sdS + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+        st_shared_v4(addr, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                     pack_bf16x2(g[6], g[7]));
+      }
+      // the dT_w MMAs read 128 operand columns (M = 128): zero what lies beyond tw_pad
+      for (int c0 = a.tw_pad + half * 8; c0 < 128; c0 += 16) {
+        const uint32_t addr = sdS + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+        st_shared_v4(addr, 0u, 0u, 0u, 0u);
       }
     }
     fence_proxy_async_smem();
@@ -845,8 +853,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if constexpr (PK2) {
               float t0, t1;
               unpack_f2(fma_f2(pack_u2(v0, v1), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2])), t0, t1);
-              p0 = fast_exp2(t0);
-              p1 = fast_exp2(t1);
+              exp2_pair(c >> 1, t0, t1, p0, p1);
             } else {
               const int k1 = kc + 1;
               p0 = fast_exp2(fmaf(__uint_as_float(v0), sc, hb[kc / W] + relw[kc % W]));

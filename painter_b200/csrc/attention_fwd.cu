@@ -326,8 +326,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               t1 = fmaf(__uint_as_float(v[ci & 1][c + 1]), sc, hbm[k1 / W] + relw[k1 % W]);
             }
             mx = fmaxf(mx, fmaxf(t0, t1));
-            p[c] = fast_exp2(t0);
-            p[c + 1] = fast_exp2(t1);
+            if constexpr (PK2) {
+              exp2_pair(c >> 1, t0, t1, p[c], p[c + 1]);
+            } else {
+              p[c] = fast_exp2(t0);
+              p[c + 1] = fast_exp2(t1);
+            }
             if constexpr (PK2) l2 = add_f2(l2, pack_f2(p[c], p[c + 1]));
             else l_tile += p[c] + p[c + 1];
           }

@@ -351,6 +351,41 @@ __device__ __forceinline__ f32x2 mul_f2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// exp2 of a pair of scores.  The MUFU pipe (16 ex2 / clk / SM) is what bounds the softmax warps of the attention
+// kernels at head dim 64 - one exponential per score against 4 x 64 tensor-core FLOP - so a compile-time fraction of
+// the pairs (PK_EXP_POLY_MASK, one bit per pair position modulo 4) is evaluated on the FMA / ALU pipes instead:
+// Cody-Waite range reduction with the round-to-nearest magic constant (x = n + f, |f| <= 0.5), a degree-3 minimax
+// polynomial for 2^f (max rel. error 7.5e-5 - far below the bf16 rounding of P / dS) and the exponent added as an
+// integer.  Arguments are clamped at -126 (masked scores arrive as -inf and must come out as ~0).
+#ifndef PK_EXP_POLY_MASK
+#define PK_EXP_POLY_MASK 0x0
+#endif
+__device__ __forceinline__ void exp2_poly_pair(float t0, float t1, float& e0, float& e1) {
+  t0 = fmaxf(t0, -126.0f);
+  t1 = fmaxf(t1, -126.0f);
+  const f32x2 x2 = pack_f2(t0, t1);
+  const f32x2 z2 = add_f2(x2, pack_f2(12582912.0f, 12582912.0f));          // n in the low mantissa bits
+  const f32x2 n2 = add_f2(z2, pack_f2(-12582912.0f, -12582912.0f));         // float(n)
+  const f32x2 f2 = fma_f2(n2, pack_f2(-1.0f, -1.0f), x2);                   // f = x - n
+  f32x2 p2 = fma_f2(pack_f2(0.055170804f, 0.055170804f), f2, pack_f2(0.24260928f, 0.24260928f));
+  p2 = fma_f2(p2, f2, pack_f2(0.69326097f, 0.69326097f));
+  p2 = fma_f2(p2, f2, pack_f2(0.99992818f, 0.99992818f));
+  float z0, z1, p0, p1;
+  unpack_f2(z2, z0, z1);
+  unpack_f2(p2, p0, p1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(z0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(z1) << 23));
+}
+// pair_idx must be a compile-time constant after unrolling (the branch folds away)
+__device__ __forceinline__ void exp2_pair(int pair_idx, float t0, float t1, float& e0, float& e1) {
+  if (((PK_EXP_POLY_MASK) >> (pair_idx & 3)) & 1) {
+    exp2_poly_pair(t0, t1, e0, e1);
+  } else {
+    e0 = fast_exp2(t0);
+    e1 = fast_exp2(t1);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -47,5 +47,30 @@ for rep in range(2):   # first pass warms up (ncu: use -s to skip it)
         o, lse = ops.attn_fwd(qkv, th, tw, B, heads, h, w)
         do = (torch.randn(B * N, C, device=dev) * 0.5).bfloat16()
         ops.attn_bwd(qkv, o, do, lse, th, tw, B, heads, h, w)
+    if "stream" in which:
+        # HBM-bound kernels of the step at their real sizes (B = 8)
+        g = torch.randn(C, device=dev)
+        bta = torch.randn(C, device=dev)
+        xf = torch.randn(M, C, device=dev)
+        u, mean, rstd = ops.layernorm_fwd(xf, g, bta, 1e-6)                            # LN fwd (fp32 -> bf16)
+        dyb = torch.randn(M, C, device=dev).bfloat16()
+        dres = torch.randn(M, C, device=dev)
+        dg, db, cs = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        rs = torch.ones(8, device=dev)
+        ops.layernorm_bwd(dyb, xf, mean, rstd, g, dg, db, dres=dres, cast=(rs, N, cs))   # fused LN bwd (+ bf16 cast + colsum)
+        ops.layernorm_bwd(dyb, xf, mean, rstd, g, dg, db, dres=dres)                     # plain LN bwd
+        ops.colsum_bf16(x4)                                                            # bias gradient of fc1
+        from painter_b200.optim import FusedAdamW
+        big = [torch.nn.Parameter(torch.randn(4096, 1024, device=dev)) for _ in range(24)]
+        for p_ in big:
+            p_.grad = torch.randn_like(p_)
+        opt = FusedAdamW(big, lr=1e-4, weight_decay=0.05)
+        opt.step()                                                                     # 100 M parameters: 2.8 GB of traffic
+        c1 = torch.randn(8 * 896 * 448, 64, device=dev).bfloat16().view(8, 896, 448, 64)
+        tg = torch.randn(8, 3, 896, 448, device=dev)
+        mk = (torch.rand(8, N, device=dev) < 0.5).to(torch.uint8)
+        hp = torch.randn(392, device=dev) * 0.1
+        ops.decoder_head_bwd(c1, tg, mk, torch.ones_like(tg), torch.ones(8, device=dev) * 1e-6,
+                             torch.ones(1, device=dev), hp, 16, 0)                     # decoder head backward
     torch.cuda.synchronize()
 print("done")

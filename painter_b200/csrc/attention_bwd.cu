@@ -444,7 +444,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             float t0, t1;
             unpack_f2(t2, t0, t1);
             float p0, p1;
-            exp2_pair(c >> 1, t0, t1, p0, p1);
+            exp2_pair<PK_EXP_POLY_MASK_DQ>(c >> 1, t0, t1, p0, p1);
             const f32x2 d2 = mul_f2(pack_f2(p0, p1), add_f2(pack_u2(w0, w1), nd2));
             gh2[kc / W] = add_f2(gh2[kc / W], d2);
             gw2[(kc % W) / 2] = add_f2(gw2[(kc % W) / 2], d2);
@@ -853,7 +853,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if constexpr (PK2) {
               float t0, t1;
               unpack_f2(fma_f2(pack_u2(v0, v1), sc2, add_f2(hb2[kc / W], relw2[(kc % W) / 2])), t0, t1);
-              exp2_pair(c >> 1, t0, t1, p0, p1);
+              exp2_pair<PK_EXP_POLY_MASK_DKV>(c >> 1, t0, t1, p0, p1);
             } else {
               const int k1 = kc + 1;
               p0 = fast_exp2(fmaf(__uint_as_float(v0), sc, hb[kc / W] + relw[kc % W]));

@@ -327,7 +327,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             mx = fmaxf(mx, fmaxf(t0, t1));
             if constexpr (PK2) {
-              exp2_pair(c >> 1, t0, t1, p[c], p[c + 1]);
+              exp2_pair<PK_EXP_POLY_MASK_FWD>(c >> 1, t0, t1, p[c], p[c + 1]);
             } else {
               p[c] = fast_exp2(t0);
               p[c + 1] = fast_exp2(t1);

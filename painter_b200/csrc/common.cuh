@@ -351,14 +351,22 @@ __device__ __forceinline__ f32x2 mul_f2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// exp2 of a pair of scores.  The MUFU pipe (16 ex2 / clk / SM) is what bounds the softmax warps of the attention
-// kernels at head dim 64 - one exponential per score against 4 x 64 tensor-core FLOP - so a compile-time fraction of
-// the pairs (PK_EXP_POLY_MASK, one bit per pair position modulo 4) is evaluated on the FMA / ALU pipes instead:
+// exp2 of a pair of scores.  Where a softmax pass is bound by the MUFU pipe (16 ex2 / clk / SM) rather than by issue
+// slots, a compile-time fraction of the pairs (mask: one bit per pair position modulo 4) is evaluated on the FMA / ALU
+// pipes instead (measured, B = 8 geometry, scripts/attn_poly_sweep.sh: the first pass of the dK/dV kernel - which does
+// nothing but exponentials - gains 8 % at 25 %; the forward and the dQ kernel are issue-bound and lose, so they keep
+// mask 0):
 // Cody-Waite range reduction with the round-to-nearest magic constant (x = n + f, |f| <= 0.5), a degree-3 minimax
 // polynomial for 2^f (max rel. error 7.5e-5 - far below the bf16 rounding of P / dS) and the exponent added as an
 // integer.  Arguments are clamped at -126 (masked scores arrive as -inf and must come out as ~0).
-#ifndef PK_EXP_POLY_MASK
-#define PK_EXP_POLY_MASK 0x0
+#ifndef PK_EXP_POLY_MASK_FWD
+#define PK_EXP_POLY_MASK_FWD 0x0
+#endif
+#ifndef PK_EXP_POLY_MASK_DQ
+#define PK_EXP_POLY_MASK_DQ 0x0
+#endif
+#ifndef PK_EXP_POLY_MASK_DKV
+#define PK_EXP_POLY_MASK_DKV 0x8
 #endif
 __device__ __forceinline__ void exp2_poly_pair(float t0, float t1, float& e0, float& e1) {
   t0 = fmaxf(t0, -126.0f);
@@ -377,8 +385,9 @@ __device__ __forceinline__ void exp2_poly_pair(float t0, float t1, float& e0, fl
   e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(z1) << 23));
 }
 // pair_idx must be a compile-time constant after unrolling (the branch folds away)
+template <int MASK>
 __device__ __forceinline__ void exp2_pair(int pair_idx, float t0, float t1, float& e0, float& e1) {
-  if (((PK_EXP_POLY_MASK) >> (pair_idx & 3)) & 1) {
+  if ((MASK >> (pair_idx & 3)) & 1) {
     exp2_poly_pair(t0, t1, e0, e1);
   } else {
     e0 = fast_exp2(t0);

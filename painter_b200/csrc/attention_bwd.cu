@@ -809,6 +809,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < num_q; ++i) {
       // packed fp32 pairs + -inf masking as in kernel A (invalid key rows of this tile / invalid query rows -> p = 0)
       constexpr bool PK2 = (W % 2 == 0);
+      if (row == 0 && half == 0) AB_TRACE(1, 1, i, 5);
       const bool valid = valid_n;
       const float lse = lse_n, delta = delta_n;
       float hb[RH], relw[W];
@@ -825,6 +826,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < W / 2; ++j) relw2[j] = pack_f2(relw[2 * j], relw[2 * j + 1]);
       }
       const f32x2 sc2 = pack_f2(sc, sc), nd2 = pack_f2(-delta, -delta);
+      if (row == 0 && half == 0 && ab_tr) {
+        // debug timeline only: force the operands of this tile to have arrived before the stamp
+        float chk = lse + delta + hb[0] + relw[0] + relw[W - 1];
+        asm volatile("" ::"f"(chk));
+        AB_TRACE(1, 1, i, 6);
+      }
       if (i + 1 < num_q) fetch(i + 1);
       if (row == 0 && half == 0) AB_TRACE(1, 1, i, 0);
       mbar_wait(bar_s + 8 * (i & 1), (i >> 1) & 1);

@@ -17,8 +17,8 @@ torch.cuda.synchronize()
 _lib.lib().pk_attn_set_trace(None)
 t = buf.cpu().view(3, 16, 8)
 t0 = int(t[1, 0, 0])
-names = {0: ["ke_seen", "ve_seen"], 1: ["loop_top", "kf_seen", "qk_issued", "p_seen", "vf_seen"],
-         2: ["before_wait_s", "s_seen", "softmax_done", "arrived_p"]}
+names = {0: ["ke_seen", "ve_seen"], 1: ["loop_top", "fa_seen", "fb_seen", "vf_seen", "p_seen"],
+         2: ["tile_top", "sa_seen", "sb_seen", "softmax_done", "arrived_p"]}
 for j in range(14):
     line = f"tile {j:2d}: "
     for role in (1, 2, 0):
@@ -44,9 +44,9 @@ for kern, kn in ((0, "dq "), (1, "dkv")):
     t0 = int(t2[kern, 0, 0, 0])
     for j in range(14 if kern == 0 else 13):
         m = [int(t2[kern, 0, j, e]) - t0 for e in range(6)]
-        sx = [int(t2[kern, 1, j, e]) - t0 for e in range(5)]
+        sx = [int(t2[kern, 1, j, e]) - t0 for e in range(7)]
         print(f"{kn} it {j:2d}: mma top={m[0]:7d} s_next_issued={m[2]:7d} p_seen={m[3]:7d} dp_next_issued={m[5]:7d} "
-              f"acc_issued={m[4]:7d} | smx wait={sx[0]:7d} bar_s_seen={sx[4]:7d} bar_dp_seen={sx[1]:7d} done={sx[2]:7d} arrived={sx[3]:7d}")
+              f"acc_issued={m[4]:7d} | smx top={sx[5]:7d} operands_in={sx[6]:7d} wait={sx[0]:7d} bar_s_seen={sx[4]:7d} bar_dp_seen={sx[1]:7d} done={sx[2]:7d} arrived={sx[3]:7d}")
 
 ph = [int(t2[0, 1, 15, e]) - int(t2[0, 0, 0, 0]) for e in range(8)]
 print("dq phases (cycles rel. to mma top of it 0): start, delta_done, relw_done, relh_done, loop_done, ep1_done, ep2_done, end:", ph)

@@ -282,6 +282,29 @@ def test_attention_fwd_bwd_vs_reference_math(B, heads, h, w):
     assert relmax(dTh, t32.grad[:2 * h - 1]) < 2e-2 and relmax(dTw, w32.grad[:2 * w - 1]) < 2e-2
 
 
+@pytest.mark.parametrize("jump", [70.0, 1100.0])
+def test_attention_fwd_running_max_rescale_paths(jump):
+    """Scores that keep growing along the key axis: every key tile (and the second column half of every tile) outgrows
+    the running reference point by more than 2^8 - resp. by more than 2^127, where exp2 of the stale reference point
+    overflows - so the forward has to move the reference point and rescale O, l and the P half already written."""
+    from painter_b200 import ops
+    B, heads, h, w = 1, 2, 16, 28
+    N, C = h * w, heads * 64
+    g = torch.Generator(device="cpu").manual_seed(5)
+    q = 1.0 + 0.02 * torch.randn(B * N, heads, 64, generator=g)
+    u = torch.arange(N)
+    c = (u // 112).float() * jump + ((u % 112) >= 64).float() * 0.8 * jump + 3.0 * torch.randn(N, generator=g)
+    k = (c / 64.0)[:, None, None].expand(N, heads, 64).repeat(B, 1, 1)
+    v = torch.randn(B * N, heads, 64, generator=g)
+    qkv = torch.stack([q, k, v], 1).reshape(B * N, 3 * C).to(DEV).bfloat16()
+    th = ops.relpos_table_bf16(torch.randn(2 * h - 1, 64, device=DEV) * 0.3)
+    tw = ops.relpos_table_bf16(torch.randn(2 * w - 1, 64, device=DEV) * 0.3)
+    out, lse = ops.attn_fwd(qkv, th, tw, B, heads, h, w)
+    ro = _ref_attn(qkv, th, tw, B, heads, h, w)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert relmax(out, ro) < 1e-2
+
+
 def test_attention_rows_are_convex_combinations_at_full_size():
     """Property at B=8 x 16 heads x 1568 tokens: with V = const the output equals that constant for every row,
     whatever the scores / bias (softmax rows sum to one)."""

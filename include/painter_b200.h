@@ -210,6 +210,9 @@ int pk_droppath_scales(const void* r, int dtype_code, const float* keep, float* 
 /* Persistent kernels (the tcgen05 GEMMs) use at most `n` SMs (0 = all): leaves room for a concurrent NCCL kernel
  * so that statically partitioned tiles never run as a second wave (multi-GPU backward).  Returns the old value. */
 int pk_set_sm_budget(int n);
+/* Programmatic dependent launch of the library's hot kernels (default on; PK_PDL=0 in the environment or
+   pk_set_pdl(0) turns the launch attribute off).  Returns the previous setting. */
+int pk_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Inference pre/post-processing on the device.  Replaces the numpy / torch-CPU arithmetic around the

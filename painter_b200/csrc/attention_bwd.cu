@@ -151,6 +151,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem = *holder_gen;
   // S / dP double-buffered: buffer b at columns 224 b (S) and 224 b + 112 (dP); dQ accumulator at 448
   const uint32_t tS = tmem, tdQ = tmem + 448;
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h); no global access above this line
+  pdl_wait();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -673,6 +675,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // processed; dP(i+1) reuses S(i)'s buffer as soon as the softmax warps have finished their first pass (p = exp2(.)
   // needs S only), so neither score MMA of the next tile waits for the end of the current one.
   const uint32_t tS = tmem, tdV = tmem + 336, tdK = tmem + 400;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -981,6 +985,8 @@ __global__ void __launch_bounds__(1024)
 attn_dt_reduce_kernel(const float* __restrict__ ws, int nctas, int rows, int rows_h, float* __restrict__ dTh,
                       float* __restrict__ dTw) {
   __shared__ float red[16][64];
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x, c = threadIdx.x;
   const size_t slice = static_cast<size_t>(rows) * 64;
   const float* p = ws + static_cast<size_t>(r) * 64 + c;
@@ -1010,6 +1016,8 @@ attn_dt_reduce_kernel(const float* __restrict__ ws, int nctas, int rows, int row
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
                   float* __restrict__ delta, int B, int N, int heads) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t groups = static_cast<size_t>(B) * N * heads;
   const size_t g = idx >> 3;
@@ -1085,8 +1093,8 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     const size_t threads = static_cast<size_t>(B) * N * heads * 8;
-    attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(O), static_cast<const __nv_bfloat16*>(dO), delta, B, N, heads);
+    launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, st,
+               static_cast<const __nv_bfloat16*>(O), static_cast<const __nv_bfloat16*>(dO), delta, B, N, heads);
     PK_LAUNCH_CHECK("pk_attn_bwd(delta)");
   }
   dim3 gridA((N + AB_BM - 1) / AB_BM, heads, B);
@@ -1100,9 +1108,10 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
       cudaFuncSetAttribute(attn_bwd_dkv_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  \
       attr = true;                                                                                             \
     }                                                                                                          \
-    if (!(a.debug & 4)) attn_bwd_dq_kernel<WW><<<gridA, AB_THREADS, smemA, st>>>(tmQ, tmKV, tmdO, tmTh, tmTw, a); \
+    if (!(a.debug & 4))                                                                                        \
+      launch_pdl(attn_bwd_dq_kernel<WW>, gridA, dim3(AB_THREADS), smemA, st, tmQ, tmKV, tmdO, tmTh, tmTw, a);   \
     PK_LAUNCH_CHECK("pk_attn_bwd(dq)");                                                                        \
-    if (!(a.debug & 8)) attn_bwd_dkv_kernel<WW><<<gridB, AB_THREADS, smemB, st>>>(tmQ, tmKV, tmdO, a);          \
+    if (!(a.debug & 8)) launch_pdl(attn_bwd_dkv_kernel<WW>, gridB, dim3(AB_THREADS), smemB, st, tmQ, tmKV, tmdO, a); \
     PK_LAUNCH_CHECK("pk_attn_bwd(dkv)");                                                                       \
   } break;
   switch (w) {
@@ -1120,7 +1129,8 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   {
     const int rows = 2 * h - 1 + 2 * w - 1;
     const int nctas = static_cast<int>(gridA.x * gridA.y * gridA.z);
-    attn_dt_reduce_kernel<<<dim3(rows, DT_STRIPES), dim3(64, 16), 0, st>>>(dt_ws, nctas, rows, 2 * h - 1, dTh, dTw);
+    launch_pdl(attn_dt_reduce_kernel, dim3(rows, DT_STRIPES), dim3(64, 16), 0, st, static_cast<const float*>(dt_ws),
+               nctas, rows, 2 * h - 1, dTh, dTw);
     PK_LAUNCH_CHECK("pk_attn_bwd(dT reduce)");
   }
   return 0;

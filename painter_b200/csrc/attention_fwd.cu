@@ -103,6 +103,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
   const uint32_t tS = tmem, tO = tmem + 128;
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h): the prologue above overlaps the
+  pdl_wait();                // previous kernel's tail; nothing before this line touches global memory
 
   if (warp == 4) {
     if (lane == 0) {
@@ -476,7 +478,7 @@ extern "C" int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void
       cudaFuncSetAttribute(attn_fwd_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
       attr = true;                                                                                          \
     }                                                                                                       \
-    attn_fwd_kernel<WW><<<grid, ATT_THREADS, smem, st>>>(tmQ, tmKV, tmTh, tmTw, a);                         \
+    launch_pdl(attn_fwd_kernel<WW>, grid, dim3(ATT_THREADS), smem, st, tmQ, tmKV, tmTh, tmTw, a);           \
   } break;
   switch (w) {
     PK_ATT_LAUNCH(2)

@@ -395,6 +395,11 @@ __device__ __forceinline__ void exp2_pair(int pair_idx, float t0, float t1, floa
   }
 }
 
+// Programmatic dependent launch (host_common.h): let the next kernel of the stream be scheduled / block until the
+// previous grid has completed and flushed.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

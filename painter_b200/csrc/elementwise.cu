@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, OutT* __restrict__ out, int ldo,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C) {
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h)
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -84,6 +86,8 @@ ln_bwd_kernel(const void* __restrict__ dy_, int lddy, const float* __restrict__ 
               float* __restrict__ partials /* [gridDim.x][2C or 3C] */, int M, int C,
               const float* __restrict__ rowscale, int rows_per_group, __nv_bfloat16* __restrict__ dx_bf16) {
   __shared__ float4 xch[2][8][2 * LNB_ROWS / 4];  // [buffer][warp][s1[0..R) | s2[0..R)]
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h)
+  pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const float4 gam = reinterpret_cast<const float4*>(gamma)[tid];
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -177,6 +181,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ colsum, int C, int np) {
   __shared__ float red[8][33];
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h)
+  pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x;
   const size_t ld = static_cast<size_t>(np) * C;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -389,6 +395,8 @@ __global__ void merge_halves_bwd_kernel(const float4* __restrict__ d, float4* __
 // =============================================================================================
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h)
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 v = in[i];
@@ -405,6 +413,8 @@ __global__ void scale_cast_colsum_kernel(const float* __restrict__ in, int ldin,
                                          const float* __restrict__ rowscale, int rows_per_group,
                                          __nv_bfloat16* __restrict__ out, float* __restrict__ colsum,
                                          int M, int C) {
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h)
+  pdl_wait();
   const int c4n = C / 4;
   for (int c4 = threadIdx.x; c4 < c4n; c4 += blockDim.x) {
     float4 acc = make_float4(0, 0, 0, 0);
@@ -445,6 +455,8 @@ __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, int ldin, float* __restrict__ colsum, int M,
                    int C, int rows_per_block) {
   __shared__ float red[8][256];
+  pdl_launch_dependents();   // programmatic dependent launch (host_common.h)
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -529,11 +541,11 @@ extern "C" int pk_layernorm_fwd(const float* x, int ldx, const float* gamma, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (M + 7) / 8;
   if (out_is_bf16)
-    ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps,
-                                                      static_cast<__nv_bfloat16*>(out), ldo, mean, rstd, M, C);
+    launch_pdl(ln_fwd_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, x, ldx, gamma, beta, eps,
+               static_cast<__nv_bfloat16*>(out), ldo, mean, rstd, M, C);
   else
-    ln_fwd_kernel<float><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<float*>(out), ldo,
-                                              mean, rstd, M, C);
+    launch_pdl(ln_fwd_kernel<float>, dim3(grid), dim3(256), 0, st, x, ldx, gamma, beta, eps, static_cast<float*>(out),
+               ldo, mean, rstd, M, C);
   PK_LAUNCH_CHECK("pk_layernorm_fwd");
   return 0;
 }
@@ -555,14 +567,16 @@ extern "C" int pk_layernorm_bwd(const void* dy, int dy_is_bf16, int lddy, const 
   PK_CHECK(C % 128 == 0 && C <= 1024 && lddy % 4 == 0 && ldx % 4 == 0, "pk_layernorm_bwd: bad C=%d", C);
   const int grid = ln_bwd_grid(M);
   if (dy_is_bf16)
-    ln_bwd_kernel<false, true><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
-        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, nullptr, 0, nullptr);
+    launch_pdl(ln_bwd_kernel<false, true>, dim3(grid), dim3(C / 4), 0, static_cast<cudaStream_t>(stream), dy, lddy, x,
+               ldx, mean, rstd, gamma, dres, dx, workspace, M, C, static_cast<const float*>(nullptr), 0,
+               static_cast<__nv_bfloat16*>(nullptr));
   else
-    ln_bwd_kernel<false, false><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
-        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, nullptr, 0, nullptr);
+    launch_pdl(ln_bwd_kernel<false, false>, dim3(grid), dim3(C / 4), 0, static_cast<cudaStream_t>(stream), dy, lddy, x,
+               ldx, mean, rstd, gamma, dres, dx, workspace, M, C, static_cast<const float*>(nullptr), 0,
+               static_cast<__nv_bfloat16*>(nullptr));
   PK_LAUNCH_CHECK("pk_layernorm_bwd");
-  ln_bwd_reduce_kernel<<<2 * C / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
-                                                                                        dbeta, nullptr, C, 2);
+  launch_pdl(ln_bwd_reduce_kernel, dim3(2 * C / 32), dim3(32, 8), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const float*>(workspace), grid, dgamma, dbeta, static_cast<float*>(nullptr), C, 2);
   PK_LAUNCH_CHECK("pk_layernorm_bwd(reduce)");
   return 0;
 }
@@ -580,16 +594,16 @@ extern "C" int pk_layernorm_bwd_cast(const void* dy, int dy_is_bf16, int lddy, c
   int grid = sm_count() * 2;   // the fused variant keeps 2 blocks per SM resident (<= ln_bwd_grid(M): workspace fits)
   if (grid > (M + LNB_ROWS - 1) / LNB_ROWS) grid = (M + LNB_ROWS - 1) / LNB_ROWS;
   if (dy_is_bf16)
-    ln_bwd_kernel<true, true><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
-        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
-        static_cast<__nv_bfloat16*>(dx_bf16));
+    launch_pdl(ln_bwd_kernel<true, true>, dim3(grid), dim3(C / 4), 0, static_cast<cudaStream_t>(stream), dy, lddy, x,
+               ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
+               static_cast<__nv_bfloat16*>(dx_bf16));
   else
-    ln_bwd_kernel<true, false><<<grid, C / 4, 0, static_cast<cudaStream_t>(stream)>>>(
-        dy, lddy, x, ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
-        static_cast<__nv_bfloat16*>(dx_bf16));
+    launch_pdl(ln_bwd_kernel<true, false>, dim3(grid), dim3(C / 4), 0, static_cast<cudaStream_t>(stream), dy, lddy, x,
+               ldx, mean, rstd, gamma, dres, dx, workspace, M, C, rowscale, rows_per_group,
+               static_cast<__nv_bfloat16*>(dx_bf16));
   PK_LAUNCH_CHECK("pk_layernorm_bwd_cast");
-  ln_bwd_reduce_kernel<<<3 * C / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(workspace, grid, dgamma,
-                                                                                        dbeta, colsum, C, 3);
+  launch_pdl(ln_bwd_reduce_kernel, dim3(3 * C / 32), dim3(32, 8), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const float*>(workspace), grid, dgamma, dbeta, colsum, C, 3);
   PK_LAUNCH_CHECK("pk_layernorm_bwd_cast(reduce)");
   return 0;
 }
@@ -673,8 +687,8 @@ extern "C" int pk_merge_halves_bwd(const float* d, float* out, long long half_el
 
 extern "C" int pk_cast_bf16(const float* in, void* out_bf16, long long n, void* stream) {
   PK_CHECK(in && out_bf16 && n % 4 == 0, "pk_cast_bf16: bad args (n must be a multiple of 4)");
-  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out_bf16), n / 4);
+  launch_pdl(cast_bf16_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out_bf16), static_cast<size_t>(n / 4));
   PK_LAUNCH_CHECK("pk_cast_bf16");
   return 0;
 }
@@ -687,8 +701,8 @@ extern "C" int pk_scale_cast_colsum(const float* in, int ldin, const float* rows
   if (tx > 256) tx = 256;
   int grid = sm_count() * 4;
   if (grid > (M + 3) / 4) grid = (M + 3) / 4;
-  scale_cast_colsum_kernel<<<grid, tx, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, ldin, rowscale, rows_per_group, static_cast<__nv_bfloat16*>(out_bf16), colsum, M, C);
+  launch_pdl(scale_cast_colsum_kernel, dim3(grid), dim3(tx), 0, static_cast<cudaStream_t>(stream), in, ldin, rowscale,
+             rows_per_group, static_cast<__nv_bfloat16*>(out_bf16), colsum, M, C);
   PK_LAUNCH_CHECK("pk_scale_cast_colsum");
   return 0;
 }
@@ -697,8 +711,8 @@ extern "C" int pk_colsum_bf16(const void* in_bf16, int ldin, float* colsum, int 
   PK_CHECK(in_bf16 && colsum && C % 8 == 0 && ldin % 8 == 0, "pk_colsum_bf16: bad args");
   const int rpb = 256;
   dim3 grid((C + 255) / 256, (M + rpb - 1) / rpb);
-  colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in_bf16), ldin, colsum, M, C, rpb);
+  launch_pdl(colsum_bf16_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(in_bf16), ldin, colsum, M, C, rpb);
   PK_LAUNCH_CHECK("pk_colsum_bf16");
   return 0;
 }

@@ -118,6 +118,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *holder_gen;
+  // the prologue above overlaps the tail of the previous kernel (programmatic dependent launch, host_common.h)
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -200,29 +203,72 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int eg = warp >> 2;  // column group: this warp owns the 64-column blocks with (c0 / 64) % 2 == eg
     uint32_t it = 0;
     float* stg = stg_gen + warp * (32 * STG_LD);
+    // per-warp copy of the bias values of the (up to four) 32-column chunks this warp handles in a tile: fetched with
+    // one coalesced load per lane BEFORE the accumulator is waited for, read back as shared-memory broadcasts
+    float* bias_s = stg_gen + GEMM_EPI_WARPS * (32 * STG_LD) + warp * 128;
+    // The accumulator chunk of step i+1 is loaded from TMEM while chunk i is processed where the register budget
+    // allows it (the fp32-aux epilogues hold two prefetched aux chunks instead; pipelining those too spills and
+    // measured 3 % slower, scripts/time_gemms.py).
+    constexpr bool PIPE = (KIND == PK_EPI_BF16 || KIND == PK_EPI_GELU || KIND == PK_EPI_PIXSHUF);
     GemmSched sch;
     sch.init(g, tiles_mn, num_kb, cid, ncl);
     int mn, kb0, kb1;
     for (; sch.next(mn, kb0, kb1); ++it) {
       int m_blk, n_blk;
-        gemm_tile_coords(g, mn, m_blk, n_blk);
+      gemm_tile_coords(g, mn, m_blk, n_blk);
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      const bool has_bias = g.epi.bias != nullptr;
+      float4 bias_v = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        // lane l: chunk (l >> 3) of this warp's chunk list {eg*64, eg*64+32, eg*64+128, eg*64+160}, 4 floats
+        const int ch = lane >> 3;
+        const int ccol = eg * 64 + (ch & 1) * 32 + (ch >> 1) * 128;
+        if (has_bias && ccol < BN)
+          bias_v = __ldg(reinterpret_cast<const float4*>(g.epi.bias + n_blk * BN + ccol + (lane & 7) * 4));
+      }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
+      if (has_bias) {
+        *reinterpret_cast<float4*>(bias_s + lane * 4) = bias_v;
+        __syncwarp();
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + ew * 32;
       EpiAux auxA, auxB;   // explicit ping-pong (BN is a multiple of 64): keeps both in registers
       if (eg * 64 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + eg * 64, auxA);
-      for (int c0 = eg * 64; c0 < BN; c0 += 128) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c0, v);
-        gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 32, auxB);
-        tmem_wait_ld();
-        gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, v, auxA);
-        tmem_ld_x32(taddr + c0 + 32, v);
-        if (c0 + 128 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 128, auxA);
-        tmem_wait_ld();
-        gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0 + 32, v, auxB);
+      if constexpr (PIPE) {
+        uint32_t vA[32], vB[32];
+        if (eg * 64 < BN) tmem_ld_x32(taddr + eg * 64, vA);
+        int k = 0;
+        for (int c0 = eg * 64; c0 < BN; c0 += 128, ++k) {
+          tmem_wait_ld();
+          tmem_ld_x32(taddr + c0 + 32, vB);
+          gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 32, auxB);
+          gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, vA, auxA,
+                                    has_bias ? bias_s + (2 * k) * 32 : nullptr);
+          tmem_wait_ld();
+          if (c0 + 128 < BN) {
+            tmem_ld_x32(taddr + c0 + 128, vA);
+            gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 128, auxA);
+          }
+          gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0 + 32, vB, auxB,
+                                    has_bias ? bias_s + (2 * k + 1) * 32 : nullptr);
+        }
+      } else {
+        int k = 0;
+        for (int c0 = eg * 64; c0 < BN; c0 += 128, ++k) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c0, v);
+          gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 32, auxB);
+          tmem_wait_ld();
+          gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0, v, auxA,
+                                    has_bias ? bias_s + (2 * k) * 32 : nullptr);
+          tmem_ld_x32(taddr + c0 + 32, v);
+          if (c0 + 128 < BN) gemm_epilogue_prefetch<KIND>(g.epi, row0, g.M, n_blk * BN + c0 + 128, auxA);
+          tmem_wait_ld();
+          gemm_epilogue_chunk<KIND>(g.epi, stg, row0, g.M, n_blk * BN + c0 + 32, v, auxB,
+                                    has_bias ? bias_s + (2 * k + 1) * 32 : nullptr);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -257,7 +303,7 @@ int launch_gemm2(const void* A, const void* B, int lda, int ldb, GemmArgs& g, cu
   if (!make_tmap_bf16(&tmB, B, 2, dims, strides, box)) return 3;
 
   const size_t smem = 1024 + static_cast<size_t>(g.stages) * (GEMM_A_BYTES + (g.BN / 2) * 128) + 256 +
-                      GEMM_EPI_WARPS * 32 * STG_LD * sizeof(float);
+                      GEMM_EPI_WARPS * 32 * STG_LD * sizeof(float) + GEMM_EPI_WARPS * 128 * sizeof(float);
   const int total = g.num_m_tiles * g.num_n_tiles * g.splits;
   int clusters = sm_count() / 2;
   if (g.streamk_units > 0) {
@@ -266,19 +312,8 @@ int launch_gemm2(const void* A, const void* B, int lda, int ldb, GemmArgs& g, cu
   } else if (clusters > total) {
     clusters = total;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  PdlLaunch L(dim3(2 * clusters), dim3(GEMM_THREADS), smem, st, 2);
+  cudaLaunchConfig_t& cfg = L.cfg;
 #define PK_GEMM2_CASE(KK)                                                                                       \
   case KK: {                                                                                                    \
     static bool attr_set = false;                                                                               \

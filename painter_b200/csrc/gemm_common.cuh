@@ -41,7 +41,7 @@ struct HeadArgs {
 
 // operand ring depth that fits beside the 8 epilogue staging tiles
 __host__ inline int gemm_stages_for(int stage_bytes) {
-  const int budget = 227 * 1024 - 1024 - 256 - GEMM_EPI_WARPS * 32 * 36 * 4;
+  const int budget = 227 * 1024 - 1024 - 256 - GEMM_EPI_WARPS * 32 * 36 * 4 - GEMM_EPI_WARPS * 128 * 4;
   int st = budget / stage_bytes;
   return st > 8 ? 8 : st;
 }
@@ -272,9 +272,12 @@ __device__ __forceinline__ void gemm_epilogue_prefetch(const PkEpilogue& e, int 
   }
 }
 
+// bias_s: optional shared-memory copy of the 32 bias values of this chunk (staged by the caller at tile start, so
+// that the chunk does not start with a global-memory round trip); nullptr = read e.bias through the read-only cache.
 template <int KIND>
 __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* stg, int row0, int M, int col,
-                                                    const uint32_t (&v)[32], const EpiAux& aux) {
+                                                    const uint32_t (&v)[32], const EpiAux& aux,
+                                                    const float* bias_s = nullptr) {
   const int lane = threadIdx.x & 31;
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
   const int cc = col + c4;
@@ -287,11 +290,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
     if (KIND == PK_EPI_RESID && e.rowscale != nullptr && row < M) sc *= __ldg(e.rowscale + row / e.rows_per_group);
     float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
     if (e.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col);
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s != nullptr ? bias_s : e.bias + col);
       const float bsc = KIND == PK_EPI_RESID ? sc / e.alpha : 1.0f;  // rowscale also multiplies the bias
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 b = __ldg(b4 + q);
+        const float4 b = bias_s != nullptr ? b4[q] : __ldg(b4 + q);
         srow[q] = make_float4(fmaf(__uint_as_float(v[q * 4 + 0]), sc, b.x * bsc),
                               fmaf(__uint_as_float(v[q * 4 + 1]), sc, b.y * bsc),
                               fmaf(__uint_as_float(v[q * 4 + 2]), sc, b.z * bsc),

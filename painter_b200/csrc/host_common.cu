@@ -1,6 +1,7 @@
 #include "host_common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "../../include/painter_b200.h"
@@ -34,6 +35,18 @@ int sm_count() {
   if (b > 0 && b < n) n = b & ~1;
   return n < 2 ? 2 : n;
 }
+
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("PK_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+int set_pdl(int on) { return g_pdl.exchange(on ? 1 : 0); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -92,4 +105,5 @@ int pk_version(void) { return 100; }
 const char* pk_last_error(void) { return pk::g_err; }
 long long pk_launch_count(void) { return pk::g_launches.load(); }
 int pk_set_sm_budget(int n) { return pk::g_sm_budget.exchange(n < 0 ? 0 : n); }
+int pk_set_pdl(int on) { return pk::set_pdl(on); }
 }

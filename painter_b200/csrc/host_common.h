@@ -5,8 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
 #include <string>
+#include <utility>
 
 namespace pk {
 
@@ -18,6 +20,48 @@ int sm_count();
 //   dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
 bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
+
+// Programmatic dependent launch.  Kernels that execute pdl_launch_dependents() + pdl_wait() (common.cuh) before their
+// first global-memory access are launched with the programmatic-stream-serialization attribute: the next such kernel
+// in the stream is scheduled while this one drains, runs its prologue (barrier init, TMEM allocation, descriptor
+// prefetch) on the SMs that have gone idle and blocks in griddepcontrol.wait until this grid has completed and its
+// writes are visible - stream semantics are unchanged, the launch gap and the prologue leave the critical path.
+// pk_set_pdl(0) / PK_PDL=0 turn the attribute off (the device-side wait is then a no-op).
+bool pdl_enabled();
+int set_pdl(int on);
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x = 0) {
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    unsigned n = 0;
+    if (cluster_x > 1) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = cluster_x;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (pdl_enabled()) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+  }
+};
+// launch a kernel that begins with pdl_launch_dependents() / pdl_wait()
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  PdlLaunch L(grid, block, smem, st);
+  return cudaLaunchKernelEx(&L.cfg, kernel, std::forward<Args>(args)...);
+}
 
 #define PK_CHECK(cond, ...)      \
   do {                           \

@@ -396,3 +396,9 @@ def droppath_scales(r, keep):
 def set_sm_budget(n):
     """Cap the SM count the persistent kernels size their grids for (0 = all SMs); returns the previous cap."""
     return int(lib().pk_set_sm_budget(int(n)))
+
+
+def set_pdl(on):
+    """Programmatic dependent launch of the hot kernels (include/painter_b200.h: pk_set_pdl); returns the previous
+    setting.  Default on (PK_PDL=0 in the environment disables it)."""
+    return int(lib().pk_set_pdl(int(bool(on))))

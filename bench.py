@@ -443,6 +443,9 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "long", "seggpt"],
                     help="train = BASELINE configs[1]/[3] (headline), long = configs[4], seggpt = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="1: the e2e step is painter_b200.train_utils.GraphedTrainStep (forward + backward + AdamW as one "
+                         "CUDA-graph replay; N = 1 with the pk optimizer); 0: the reference loop's eager launches")
     ap.add_argument("--no-optimizer", action="store_true", help="diagnostic only; the reported step includes AdamW")
     args = ap.parse_args()
     if args.workload == "seggpt":
@@ -546,6 +549,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # End to end the step runs the way a user of painter_b200 runs it: train_utils.GraphedTrainStep = the same
+    # forward + backward + AdamW captured once and replayed as ONE CUDA graph per iteration (single GPU, FusedAdamW).
+    # The device-resident region below stays eager - its GEMM launches carry CUDA events - and so does the reference
+    # loop reported next to the e2e figure.  (Measured: the replay is worth 0.5-0.8 % here; the eager step is already
+    # GPU-bound, its ~2.7 us kernel boundaries are not launch latency - profiles/r02_step_timeline_warm.txt.)
+    gstep = None
+    if args.graph and world == 1 and args.optimizer == "pk" and not args.no_optimizer:
+        from painter_b200.train_utils import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt)
+
     for _ in range(W_steps):
         step(resident, False)
     sync()
@@ -613,11 +626,31 @@ def main():
         sync()
         return a.elapsed_time(b), seen
 
+    def run_e2e_graph(n):
+        """The same iteration through the graphed public API: pinned-host batch copied into the step's static device
+        buffers, one graph replay, loss.item() and torch.cuda.synchronize() every step."""
+        seen = []
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            loss = gstep(*host)
+            seen.append(loss.item())
+            torch.cuda.synchronize()
+        b.record()
+        sync()
+        return a.elapsed_time(b), seen
+
     run_e2e(True, 2)        # untimed: first-use costs of the loop (stream / buffer creation) are not steady state
     run_e2e(False, 2)
     ms_e2e, seen = run_e2e(True, args.steps)
     ms_e2e_pipe, _ = run_e2e(False, args.steps)
     last_loss = seen[-1]
+    ms_e2e_eager = ms_e2e
+    if gstep is not None:
+        run_e2e_graph(2)
+        ms_e2e, seen_g = run_e2e_graph(args.steps)
+        last_loss = seen_g[-1]
     clk = clocks.stop() if rank == 0 else None
 
     ms_total, ms_e2e, ms_e2e_pipe = dist_utils.max_over_ranks([ms_total, ms_e2e, ms_e2e_pipe], device=dev)
@@ -655,6 +688,9 @@ def main():
             "config": {"workload": wl["name"],
                        "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single",
                        "tokens_per_image": wl["tokens"],
+                       "launch": "value: eager kernel launches (programmatic dependent launch between the hot kernels); "
+                                 "e2e: " + ("one CUDA-graph replay per step (train_utils.GraphedTrainStep)"
+                                            if gstep is not None else "eager"),
                        "optimizer": "none" if args.no_optimizer else (
                            "AdamW over lr_decay.param_groups_lrd groups (layer_decay 0.8, wd 0.05): " +
                            ("painter_b200.optim.FusedAdamW" if args.optimizer == "pk" else "torch fused AdamW")),
@@ -665,8 +701,14 @@ def main():
                              "no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
-                    "loop": "engine_train.train_one_epoch's (engine_train.py:52-93): pinned-host batch .to(device, "
+                    "loop": ("train_utils.GraphedTrainStep(model, optimizer)(pinned-host batch): copies into the step's "
+                             "static device buffers, one CUDA-graph replay (forward + backward + AdamW), loss.item() "
+                             "and torch.cuda.synchronize() every step") if gstep is not None else
+                            "engine_train.train_one_epoch's (engine_train.py:52-93): pinned-host batch .to(device, "
                             "non_blocking=True) on the compute stream, loss.item() and torch.cuda.synchronize() every step",
+                    "reference_loop_value": world * B / (ms_e2e_eager / args.steps / 1e3),
+                    "reference_loop_note": "engine_train.train_one_epoch's loop verbatim (eager launches, .to(device), "
+                                           "loss.item(), synchronize) driving the painter_b200 module",
                     "pipelined_value": world * B / (ms_e2e_pipe / args.steps / 1e3),
                     "pipelined_note": "same work with data_utils.DevicePrefetcher (copies one step ahead on a side "
                                       "stream) and each step's loss read back one step later (no per-step drain)"},

@@ -205,6 +205,11 @@ int pk_opt_chunk_elems(void);
 int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, double beta1, double beta2,
                   double eps, int step, const float* gscale, float gscale_cap, int zero_grad,
                   const float* found_inf, void* stream);
+/* pk_adamw_step for a CUDA-graph-captured training step (painter_b200.train_utils.GraphedTrainStep): the bias
+   corrections 1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t) are read from bc_dev[0..1] at run time. */
+int pk_adamw_step_graph(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, double beta1,
+                        double beta2, double eps, const float* bc_dev, const float* gscale, float gscale_cap,
+                        int zero_grad, const float* found_inf, void* stream);
 int pk_grad_sumsq(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, float* out_zeroed, void* stream);
 int pk_droppath_scales(const void* r, int dtype_code, const float* keep, float* out, int n, void* stream);
 /* Persistent kernels (the tcgen05 GEMMs) use at most `n` SMs (0 = all): leaves room for a concurrent NCCL kernel

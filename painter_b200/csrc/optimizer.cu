@@ -30,8 +30,13 @@ static_assert(sizeof(OptTensor) == sizeof(PkOptTensor), "PkOptTensor layout");
 __global__ void __launch_bounds__(256)
 adamw_kernel(const OptTensor* __restrict__ tensors, const int2* __restrict__ chunks, float b1, float omb1, float b2,
              float omb2, float eps, float inv_bc1, float inv_sqrt_bc2, const float* __restrict__ gscale,
-             float gscale_cap, int zero_grad, const float* __restrict__ found_inf) {
+             float gscale_cap, int zero_grad, const float* __restrict__ found_inf,
+             const float* __restrict__ bc_dev) {
   if (found_inf && found_inf[0] != 0.f) return;   // GradScaler semantics: an overflowed step is skipped entirely
+  if (bc_dev) {   // CUDA-graph replay: the step-dependent bias corrections come from device memory
+    inv_bc1 = bc_dev[0];
+    inv_sqrt_bc2 = bc_dev[1];
+  }
   const int2 ck = chunks[blockIdx.x];
   const OptTensor t = tensors[ck.x];
   const long long base = static_cast<long long>(ck.y) * OPT_CHUNK;
@@ -136,8 +141,25 @@ extern "C" int pk_adamw_step(const PkOptTensor* tensors_dev, const int* chunks_d
       reinterpret_cast<const OptTensor*>(tensors_dev), reinterpret_cast<const int2*>(chunks_dev),
       static_cast<float>(beta1), static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
       static_cast<float>(1.0 - beta2), static_cast<float>(eps), static_cast<float>(1.0 / bc1),
-      static_cast<float>(1.0 / sqrt(bc2)), gscale, gscale_cap, zero_grad, found_inf);
+      static_cast<float>(1.0 / sqrt(bc2)), gscale, gscale_cap, zero_grad, found_inf, nullptr);
   PK_LAUNCH_CHECK("pk_adamw_step");
+  return 0;
+}
+
+// The same update for a captured training step: the two step-dependent scalars 1 / (1 - beta1^t) and
+// 1 / sqrt(1 - beta2^t) are read from bc_dev[0..1], which the host rewrites before every replay; learning rates and
+// weight decays already live in the device table.
+extern "C" int pk_adamw_step_graph(const PkOptTensor* tensors_dev, const int* chunks_dev, int nchunks, double beta1,
+                                   double beta2, double eps, const float* bc_dev, const float* gscale,
+                                   float gscale_cap, int zero_grad, const float* found_inf, void* stream) {
+  using namespace pk;
+  PK_CHECK(tensors_dev && chunks_dev && nchunks > 0 && bc_dev, "pk_adamw_step_graph: bad arguments");
+  adamw_kernel<<<nchunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const OptTensor*>(tensors_dev), reinterpret_cast<const int2*>(chunks_dev),
+      static_cast<float>(beta1), static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
+      static_cast<float>(1.0 - beta2), static_cast<float>(eps), 1.0f, 1.0f, gscale, gscale_cap, zero_grad, found_inf,
+      bc_dev);
+  PK_LAUNCH_CHECK("pk_adamw_step_graph");
   return 0;
 }
 

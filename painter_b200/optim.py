@@ -59,10 +59,15 @@ def _tensor_table(entries, device, cache=None):
                   v.data_ptr() if v is not None else 0, w16.data_ptr() if w16 is not None else 0, p.numel(), lr, wd)
     if cache is not None:
         raw = rec.tobytes()
-        if cache.get("raw") == raw and cache["dev"].device == torch.device(device):
-            return cache["dev"]
+        dev_t = cache.get("dev")
+        if cache.get("raw") == raw and dev_t.device == torch.device(device):
+            return dev_t
         cache["raw"] = raw
-        cache["dev"] = torch.from_numpy(rec.view(np.uint8)).to(device)
+        host = torch.from_numpy(rec.view(np.uint8).copy())
+        if dev_t is not None and dev_t.device == torch.device(device) and dev_t.numel() == host.numel():
+            dev_t.copy_(host)          # same address: a captured training step keeps reading this table
+        else:
+            cache["dev"] = host.to(device)
         return cache["dev"]
     return torch.from_numpy(rec.view(np.uint8)).to(device)
 
@@ -108,6 +113,74 @@ class FusedAdamW(torch.optim.Optimizer):
             if ref is not None:
                 return ref()
         return None
+
+    # ---- CUDA-graph support (painter_b200.train_utils.GraphedTrainStep) -------------------------------------------
+    # A captured step cannot take the step count, the bias corrections or the learning rates as launch arguments:
+    # graph_prepare() does the host half of step() - state creation, step counters, the per-tensor (pointer, lr, wd)
+    # table rewritten IN PLACE, the two bias-correction scalars copied into a fixed device buffer - and
+    # graph_launch() issues the one kernel that reads them; the graph captures graph_launch(), every replay is
+    # preceded by graph_prepare().
+    @torch.no_grad()
+    def graph_prepare(self):
+        entries, key = [], None
+        arena = self._find_arena([p for g in self.param_groups for p in g["params"]])
+        for group in self.param_groups:
+            for p in group["params"]:
+                g = p.grad
+                if g is None and arena is not None and arena.owns(p):
+                    off, n, shape = arena.offsets[id(p)]   # zero_grad(set_to_none=True) between replays: the graph
+                    g = arena.slab[off:off + n].view(shape)  # still writes (and the kernel still clears) this slot
+                if g is None:
+                    continue
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    _check_fp32(p, "parameter")
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                elif torch.is_tensor(st["step"]):
+                    st["step"] = int(st["step"].item())
+                st["step"] += 1
+                k = (group["betas"][0], group["betas"][1], group["eps"], st["step"])
+                if key is None:
+                    key = k
+                elif k != key:
+                    raise RuntimeError("FusedAdamW.graph_prepare: all parameters must share betas, eps and step count")
+                _check_fp32(g, "gradient")
+                ent = getattr(p, "_pk_bf16", None)
+                w16 = ent[2] if ent is not None and ent[1] == p.data_ptr() and ent[2].device == p.device else None
+                entries.append((p, g, st["exp_avg"], st["exp_avg_sq"], w16, group["lr"], group["weight_decay"]))
+        if not entries:
+            raise RuntimeError("FusedAdamW.graph_prepare: no parameter has a gradient (run one eager step first)")
+        ids = {id(e[0]) for e in entries}
+        zero = 0
+        if arena is not None and all(id(p) in ids for p in arena.params):
+            lo = arena.slab.data_ptr()
+            hi = lo + arena.slab.numel() * 4
+            zero = int(all(lo <= e[1].data_ptr() < hi for e in entries))
+        dev = entries[0][0].device
+        b1, b2, eps, step = key
+        gp = self._graph = getattr(self, "_graph", None) or {}
+        if "bc_host" not in gp:
+            gp["bc_host"] = torch.empty(2, dtype=torch.float32).pin_memory()
+            gp["bc_dev"] = torch.empty(2, dtype=torch.float32, device=dev)
+        gp["bc_host"][0] = 1.0 / (1.0 - b1 ** step)
+        gp["bc_host"][1] = 1.0 / (1.0 - b2 ** step) ** 0.5
+        gp["bc_dev"].copy_(gp["bc_host"], non_blocking=True)
+        gp.update(chunks=_chunk_table([e[0].numel() for e in entries], dev),
+                  table=_tensor_table(entries, dev, self._tables.setdefault("graph", {})),
+                  b1=b1, b2=b2, eps=eps, zero=zero, arena=arena, params=[e[0] for e in entries])
+        return gp
+
+    @torch.no_grad()
+    def graph_launch(self):
+        gp = self._graph
+        check(lib().pk_adamw_step_graph(_ptr(gp["table"]), _ptr(gp["chunks"]), gp["chunks"].shape[0],
+                                        ctypes.c_double(gp["b1"]), ctypes.c_double(gp["b2"]),
+                                        ctypes.c_double(gp["eps"]), _ptr(gp["bc_dev"]), None, ctypes.c_float(0.0),
+                                        gp["zero"], None, _stream()), "pk_adamw_step_graph")
+        if gp["zero"]:
+            gp["arena"].mark_clean()
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=None, grad_scale_cap=0.0, found_inf=None):

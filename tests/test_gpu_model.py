@@ -240,6 +240,57 @@ def test_fused_adamw_trains_the_gemm_weights():
     assert losses[-1] < losses[0], losses
 
 
+def test_graphed_train_step_equals_eager_steps():
+    """train_utils.GraphedTrainStep: forward + backward + FusedAdamW as one CUDA-graph replay per iteration.  With
+    DropPath off (eval-mode module, as the parity tests run it) every replay must reproduce the eager step: same
+    losses, same parameters after 4 iterations with a learning rate that changes every iteration, and the warm-up
+    iterations of the capture must leave no trace (parameters / optimizer state restored)."""
+    from painter_b200.optim import FusedAdamW
+    from painter_b200.train_utils import GraphedTrainStep
+    cfg = po.PainterConfig(img_size=(128, 64), embed_dim=128, num_heads=2, decoder_embed_dim=64)
+    model, _ = build_model(cfg, 0)
+    twin, _ = build_model(cfg, 0)
+    model.eval()
+    twin.eval()
+    batches = [_to("cuda", *synth_inputs(cfg, 4, 3 + i)) for i in range(4)]
+    lrs = [2e-4, 1.5e-4, 1e-4, 0.5e-4]
+    opt_e = FusedAdamW(twin.parameters(), lr=lrs[0], betas=(0.9, 0.999), weight_decay=0.05)
+    eager = []
+    for (imgs, tgts, mask, valid), lr in zip(batches, lrs):
+        for g in opt_e.param_groups:
+            g["lr"] = lr
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, _, _ = twin(imgs, tgts, bool_masked_pos=mask, valid=valid)
+        loss.backward()
+        opt_e.step()
+        opt_e.zero_grad(set_to_none=True)
+        eager.append(loss.item())
+    opt_g = FusedAdamW(model.parameters(), lr=lrs[0], betas=(0.9, 0.999), weight_decay=0.05)
+    step = GraphedTrainStep(model, opt_g)
+    graphed = []
+    for (imgs, tgts, mask, valid), lr in zip(batches, lrs):
+        for g in opt_g.param_groups:
+            g["lr"] = lr
+        graphed.append(step(imgs, tgts, mask, valid).item())
+    assert len(step.entries) == 1
+    # the first replay sees exactly the eager step's inputs and weights; later ones differ by the summation order of
+    # the stream-K weight-gradient atomics (as two eager runs do): ~1e-5 relative on the loss after three updates
+    assert abs(eager[0] - graphed[0]) <= 1e-6 * abs(eager[0]), (eager, graphed)
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(a)), (eager, graphed)
+    ref0, _ = build_model(cfg, 0)
+    for (n, p), (_, q), (_, p0) in zip(model.named_parameters(), twin.named_parameters(), ref0.named_parameters()):
+        if p.numel() < 4096:
+            continue
+        du_g, du_e = (p.detach() - p0.detach()).double(), (q.detach() - p0.detach()).double()
+        rel = (du_g - du_e).norm().item() / (du_e.norm().item() + 1e-30)
+        assert rel <= 0.05, (n, rel)      # four Adam updates agree to a few per cent in every large tensor
+    st_g, st_e = opt_g.state[model.blocks[3].mlp.fc1.weight], opt_e.state[twin.blocks[3].mlp.fc1.weight]
+    assert st_g["step"] == st_e["step"] == 4
+    rel = (st_g["exp_avg_sq"].double() - st_e["exp_avg_sq"].double()).norm() / st_e["exp_avg_sq"].double().norm()
+    assert rel.item() <= 1e-3, rel.item()
+
+
 def test_gradient_arena_views_accumulation_and_fused_step():
     """painter_b200/arena.py: p.grad is a view of the flat arena after a backward; a second backward without
     zero_grad accumulates (scratch slab) to exactly twice the gradient; FusedAdamW consumes and clears the arena and

@@ -39,9 +39,16 @@ def test_tensor_table_carries_pointers_sizes_and_group_hyperparameters():
     cache = {}
     tab = optim._tensor_table([(p, g, m, v, w16, 3e-3, 0.05)], torch.device("cpu"), cache)
     assert optim._tensor_table([(p, g, m, v, w16, 3e-3, 0.05)], torch.device("cpu"), cache) is tab   # cached
-    assert optim._tensor_table([(p, g, m, v, w16, 4e-3, 0.05)], torch.device("cpu"), cache) is not tab  # lr changed
     raw = tab.numpy().tobytes()
     rec = PkOptTensor.from_buffer_copy(raw)
     assert (rec.p, rec.g, rec.m, rec.v, rec.n) == (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 10)
     assert rec.w16 == w16.data_ptr()
     assert abs(rec.lr - 3e-3) < 1e-9 and abs(rec.wd - 0.05) < 1e-8
+    # a changed learning rate rewrites the SAME device table (a captured training step keeps its address)
+    ptr = tab.data_ptr()
+    tab2 = optim._tensor_table([(p, g, m, v, w16, 4e-3, 0.05)], torch.device("cpu"), cache)
+    assert tab2 is tab and tab2.data_ptr() == ptr
+    assert abs(PkOptTensor.from_buffer_copy(tab2.numpy().tobytes()).lr - 4e-3) < 1e-9
+    # a different parameter list does not fit the old table: new allocation
+    tab3 = optim._tensor_table([(p, g, m, v, w16, 4e-3, 0.05), (p, g, m, v, None, 1e-3, 0.0)], torch.device("cpu"), cache)
+    assert tab3 is not tab and tab3.numel() == 2 * tab.numel()

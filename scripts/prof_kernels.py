@@ -28,7 +28,7 @@ b1 = torch.randn(C, device=dev)
 b4 = torch.randn(4 * C, device=dev)
 res = torch.randn(M, C, device=dev)
 
-for rep in range(2):   # first pass warms up (ncu: use -s to skip it)
+for rep in range(int(os.environ.get("PK_PROF_REPS", "2"))):   # first pass warms up (PK_PROF_REPS=1 under ncu: it replays anyway)
     if "gemm" in which:
         qkv = ops.gemm(x, wqkv, kind=ops.EPI_BF16, bias=b3)                       # qkv fwd
         ops.gemm(x, wproj, kind=ops.EPI_RESID, bias=b1, aux=res)                   # proj fwd

@@ -143,7 +143,7 @@ int pk_ensemble_resid(const float* a, const float* z, float* out, int G, int P, 
  * (bf16, zero-padded to th_pad/tw_pad rows, multiples of 16); w must divide 112 (2,4,7,8,14,28,56).
  * fwd: out bf16 [B*N, heads*64], lse fp32 [B*heads, N] (log2 domain, nullable).
  * bwd: dqkv bf16 like qkv; dTh [2h-1,64], dTw [2w-1,64] fp32, added to (zero-initialise);
- *      scratch: delta [B*heads*N], relh_g [B*heads*N*h], relw_g [B*heads*N*w], dt_ws
+ *      scratch: delta [B*heads*N], relh_g [B*heads*Np*h], relw_g [B*heads*Np*w] (Np = N rounded up to 128), dt_ws
  *      [pk_attn_bwd_ws_floats(B, heads, h, w)] fp32 (per-CTA partial table gradients, reduced by a
  *      second kernel instead of same-address atomics).                                                     */
 int pk_relpos_table_bf16(const float* table, void* out_bf16, int L, int Lpad, void* stream);
@@ -153,6 +153,16 @@ int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse
                 void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g, float* relw_g, float* dt_ws,
                 int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream);
 long long pk_attn_bwd_ws_floats(int B, int heads, int h, int w);
+/* Training pair: pk_attn_fwd_save additionally stores every query's log2e-scaled bias rows (rel_h / rel_w of
+ * vitdet_utils.py:113-123) in relh_g / relw_g (B*heads*Np*h resp. B*heads*Np*w floats, Np = N rounded up to 128; per
+ * 128-query tile, query row innermost); pk_attn_bwd_saved takes them as INPUTS, so its dQ kernel starts from coalesced
+ * loads instead of recomputing the two bias GEMMs and Toeplitz gathers.  Results are identical to pk_attn_fwd /
+ * pk_attn_bwd.                                                                                                  */
+int pk_attn_fwd_save(const void* qkv, const void* th, const void* tw, void* out, float* lse, float* relh_g,
+                     float* relw_g, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream);
+int pk_attn_bwd_saved(const void* qkv, const void* O, const void* dO, const float* lse, const void* th, const void* tw,
+                      void* dqkv, float* dTh, float* dTw, float* delta, const float* relh_g, const float* relw_g,
+                      float* dt_ws, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Decoder head (models_painter.py:328-333,430 decoder_pred = conv3x3 -> LayerNorm2D -> GELU -> conv1x1;

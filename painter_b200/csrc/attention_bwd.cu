@@ -59,14 +59,22 @@ struct AttnBwdArgs {
   const __nv_bfloat16* dO;   // [B*N, C]
   const float* lse;          // [B*heads, N]
   float* delta;              // [B*heads, N]
-  float* relh_g;             // [B*heads, N, h]   (log2e-scaled)
-  float* relw_g;             // [B*heads, N, W]
+  // bias rows handed from kernel A to kernel B (log2e-scaled), stored per 128-query tile with the QUERY ROW INNERMOST
+  // so that the one-thread-per-row accesses of both kernels are coalesced (a warp touches 128 / 512 contiguous bytes;
+  // with the row-major [N, W] layout every lane owned its own 112-byte row and a warp-wide load spread over ~30 cache
+  // lines - the fetch of the next tile's operands stalled kernel B's softmax warps for 400-1100 cycles per tile):
+  float* relh_g;             // [B*heads, q tiles, h, 128]
+  float* relw_g;             // [B*heads, q tiles, W/4, 128] float4   (W % 4 != 0: [B*heads, q tiles, W, 128] floats)
   __nv_bfloat16* dqkv;       // [B*N, 3C]
-  float* dt_ws;              // [CTAs of kernel A][2h-1 + 2W-1][64] fp32 partial table gradients
+  float* dt_ws;              // [CTAs of kernel A][64][2h-1 + 2W-1] fp32 partial table gradients, table row innermost:
+                             // the row owners' stores are then 128 contiguous bytes per warp (row-major slices made
+                             // every 16-byte store of a warp hit its own cache line: ~3 k cycles per CTA)
   long long* trace;          // optional debug timeline of CTA (0,0,0): [kernel][role][iter][event]
   int debug;                 // measurement aids: bit 1 trace the last (b, head) CTA instead of the first,
                              // bit 2 skip kernel A, bit 3 skip kernel B (scripts/time_attn_parts.py)
   int kv_stages;             // kernel A: K/V ring depth (3 normally; 2 when shared memory is short)
+  int rel_ready;             // relh_g / relw_g were written by the forward (pk_attn_fwd_save): kernel A loads its bias
+                             // rows instead of recomputing G_h / G_w (two MMAs + the Toeplitz gathers) and emitting them
 };
 
 // debug timeline: `ab_tr` (one predicate register per thread, set at kernel entry) selects the traced CTA, so a
@@ -104,6 +112,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                  bar_gr = bar0 + 136, bar_e = bar0 + 144, bar_er = bar0 + 152, bar_t = bar0 + 160,
                  bar_gw = bar0 + 168;  // G_w retired (single completion; bar_g completes twice and would alias)
   const uint32_t holder = bar0 + 176;
+  const uint32_t bar_e2 = bar0 + 184;  // single-phase epilogue: the table-gradient MMAs (issued by warp 9) retired
   volatile uint32_t* holder_gen =
       reinterpret_cast<volatile uint32_t*>(gen + srelh_off + a.relh_bytes + 176);
 
@@ -118,6 +127,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // TMA latency disappears from the epilogue; otherwise they land on stages 0/1 after the main loop has retired.
   const bool early_tables =
       KS == 3 && num_tiles >= 3 && static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u <= 28672u;
+  // Single-phase epilogue: when Gh^ needs at most two 64-column K-blocks (th_pad <= 128) it lives in dS buffer 0 and
+  // Gw^ in dS buffer 1, the Gw' exchange between the column halves goes through the (dead) dO tile, and ONE batch of
+  // MMAs / one TMEM read-out replaces the two dependent rounds (the epilogue was 12 k of a CTA's 48 k cycles at 56x28:
+  // profiles/r02_attn_cta_timelines.txt).
+  const bool merged_ep = a.th_pad <= 128 && static_cast<uint32_t>(W + 1) * AB_BM * 4u <= 16384u;
   const uint32_t sTh = early_tables ? sKV + static_cast<uint32_t>(num_tiles % 3) * 28672u : base + A_STH;
   const uint32_t sTw = early_tables ? sTh + static_cast<uint32_t>(a.th_pad) * 128u : base + A_STW;
 
@@ -142,6 +156,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_er, AB_SMX);
     mbar_init(bar_t, 1);
     mbar_init(bar_gw, 1);
+    mbar_init(bar_e2, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(holder, 512);
@@ -157,15 +172,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 8) {
     if (lane == 0) {
       // ------------------------------------ TMA producer ------------------------------------
-      mbar_expect_tx(bar_q, 32768u + static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u);
+      mbar_expect_tx(bar_q, 32768u + (a.rel_ready ? 0u : static_cast<uint32_t>(a.th_pad + a.tw_pad) * 128u));
       tma_load_3d(sQ, &tmQ, bar_q, head * 64, q0, b);
       tma_load_3d(sdO, &tmdO, bar_q, head * 64, q0, b);
-      tma_load_2d(sdS, &tmTh, bar_q, 0, 0);                 // T_h: th_pad <= 224 rows -> 28 KiB <= 32 KiB
-      tma_load_2d(sKV + (KS - 1) * 28672 + 14336, &tmTw, bar_q, 0, 0);  // T_w in the last stage's V buffer
+      if (!a.rel_ready) {
+        tma_load_2d(sdS, &tmTh, bar_q, 0, 0);                 // T_h: th_pad <= 224 rows -> 28 KiB <= 32 KiB
+        tma_load_2d(sKV + (KS - 1) * 28672 + 14336, &tmTw, bar_q, 0, 0);  // T_w in the last stage's V buffer
+      }
       for (int j = 0; j < num_tiles; ++j) {
         const int st = j % KS;
         if (j >= KS) mbar_wait(bar_ke + 8 * st, ((j / KS) - 1) & 1);
-        if (j == KS - 1) mbar_wait(bar_gw, 0);  // G_w MMA done with T_w (last stage's V buffer)
+        if (j == KS - 1 && !a.rel_ready) mbar_wait(bar_gw, 0);  // G_w MMA done with T_w (last stage's V buffer)
         mbar_expect_tx(bar_kf + 8 * st, 2 * AB_KT * 128);
         tma_load_3d(sKV + st * 28672, &tmKV, bar_kf + 8 * st, C + head * 64, j * AB_KT, b);
         tma_load_3d(sKV + st * 28672 + 14336, &tmKV, bar_kf + 8 * st, 2 * C + head * 64, j * AB_KT, b);
@@ -185,6 +202,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // warp-uniform control flow; the tcgen05 instructions themselves are issued by one elected lane
       mbar_wait(bar_q, 0);
       tc_fence_after();
+      if (!a.rel_ready) {
       {  // G_w = Q . T_w^T
         const uint32_t idesc = make_idesc_bf16(128, a.tw_pad, false, false);
         const uint32_t sT = sKV + (KS - 1) * 28672 + 14336;
@@ -211,6 +229,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       mbar_wait(bar_gr, 1);
       tc_fence_after();
+      }
       const uint32_t idesc_s = make_idesc_bf16(128, AB_KT, false, false);
       const uint64_t dQ0 = make_sdesc(sQ, 16, 1024), ddO0 = make_sdesc(sdO, 16, 1024);
       // Scores issuer: S/dP of tile j go out as soon as their TMEM buffer (j & 1) has been read by the softmax warps
@@ -235,6 +254,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __syncwarp();
         AB_TRACE(0, 0, j, 2);
+      }
+      if (merged_ep) {
+        // single-phase epilogue, second issuer: the 16 table-gradient MMAs go out from this (now idle) warp while
+        // warp 10 issues the 11 dQ-bias MMAs - a lone thread dispatches a short burst at 100-190 cycles per MMA
+        const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
+        mbar_wait(bar_er, 0);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int mh = 0; mh * 128 < a.th_pad; ++mh)
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tS + mh * 64, make_sdesc(sdS + (2 * mh) * 16384 + kk * 2048, 16384, 1024),
+                      make_sdesc(sQ + kk * 2048, 16, 1024), idesc_tt, kk != 0);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tS + 128, make_sdesc(sdS + 32768 + kk * 2048, 16384, 1024), make_sdesc(sQ + kk * 2048, 16, 1024),
+                    idesc_tt, kk != 0);
+          umma_commit(bar_e2);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 10) {
@@ -261,8 +300,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       if (elect_one()) umma_commit(bar_e);  // completion #1 (parity 0): main loop retired
       __syncwarp();
-      // ---- epilogue phase 1: dQ += Gh^ . T_h ; dT_h = Gh^^T . Q ----
       const uint32_t idesc_tt = make_idesc_bf16(128, 64, true, true);
+      if (merged_ep) {
+        // ---- single-phase epilogue (both Toeplitz operands fit next to each other: Gh^ in dS buffer 0, Gw^ in
+        // buffer 1): dQ += Gh^ . T_h + Gw^ . T_w here; dT_h = Gh^^T . Q -> columns [0, 128) and dT_w = Gw^^T . Q ->
+        // [128, 192) from warp 9
+        mbar_wait(bar_er, 0);
+        mbar_wait(bar_t, 0);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int kk = 0; kk < a.th_pad / 16; ++kk)
+            umma_ss(tdQ, make_sdesc(sdS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                    make_sdesc(sTh + kk * 2048, 16, 1024), idesc_dq, 1u);
+          for (int kk = 0; kk < a.tw_pad / 16; ++kk)
+            umma_ss(tdQ, make_sdesc(sdS + 32768 + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                    make_sdesc(sTw + kk * 2048, 16, 1024), idesc_dq, 1u);
+          umma_commit(bar_e);  // completion #2 (parity 1); the table-gradient MMAs: warp 9 -> bar_e2
+        }
+        __syncwarp();
+      } else {
+      // ---- epilogue phase 1: dQ += Gh^ . T_h ; dT_h = Gh^^T . Q ----
       mbar_wait(bar_er, 0);
       mbar_wait(bar_t, 0);
       tc_fence_after();
@@ -292,6 +349,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(bar_e);  // completion #3 (parity 0)
       }
       __syncwarp();
+      }
     }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
@@ -315,7 +373,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const size_t bh = static_cast<size_t>(b) * a.heads + head;
     // this CTA's slice of the table-gradient workspace: [2h-1 + 2W-1][64] fp32 partial sums (plain stores; a
     // reduction kernel adds the slices - 1664 CTAs x 10.6 K same-address atomics were ~half of this kernel's time)
-    float* ws_cta = a.dt_ws + (bh * gridDim.x + blockIdx.x) * static_cast<size_t>(2 * h - 1 + 2 * W - 1) * 64;
+    const size_t ws_rows = static_cast<size_t>(2 * h - 1 + 2 * W - 1);
+    float* ws_cta = a.dt_ws + (bh * gridDim.x + blockIdx.x) * ws_rows * 64;
 
     if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 0);
     // delta = rowsum(dO * O) comes from attn_delta_kernel (coalesced pre-pass), LSE from the forward
@@ -325,6 +384,42 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 1);
     // ---- rel_w -> registers (+ global for kernel B) ----
     float relw[W];
+    if (a.rel_ready) {
+      // bias rows kept by the forward: rel_w as W/4 coalesced 16-byte loads, this column half's rel_h values (the
+      // image rows it will meet in the main loop - no other thread reads or writes them) into the private smem row
+      const float* pw = a.relw_g + (bh * gridDim.x + blockIdx.x) * static_cast<size_t>(W) * AB_BM;
+      if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) {
+          const float4 q4 = __ldg(reinterpret_cast<const float4*>(pw) + j * AB_BM + row);
+          relw[4 * j] = q4.x; relw[4 * j + 1] = q4.y; relw[4 * j + 2] = q4.z; relw[4 * j + 3] = q4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) relw[j] = __ldg(pw + j * AB_BM + row);
+      }
+      // (batches of 32 independent read-only loads, then the smem stores: every dependent round trip to global memory
+      // costs ~2 k cycles here - a load-store-load chain per image row measured 8.7 k cycles, two batches of 16 still 7 k)
+      const float* ph = a.relh_g + (bh * gridDim.x + blockIdx.x) * static_cast<size_t>(h) * AB_BM + row;
+      constexpr int CH = RH >= 32 ? 1 : 32 / RH;   // tiles per batch (56 x 28 grid: all 14 tiles in ONE round trip)
+      for (int jb = 0; jb < num_tiles; jb += CH) {
+        float tmp[CH][RH];
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj)
+#pragma unroll
+          for (int r = 0; r < RH; ++r) {
+            const int i = (jb + jj) * R + half * RH + r;
+            tmp[jj][r] = i < h ? __ldg(ph + static_cast<size_t>(i) * AB_BM) : 0.f;
+          }
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj)
+#pragma unroll
+          for (int r = 0; r < RH; ++r) {
+            const int i = (jb + jj) * R + half * RH + r;
+            if (i < h) my_relh[i] = tmp[jj][r];
+          }
+      }
+    } else {
     {
       float* scratch = relh_gen + (static_cast<size_t>(half) * 128 + row) * 17;
       mbar_wait(bar_g, 0);
@@ -344,15 +439,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       mbar_arrive(bar_gr);
-      if (valid && half == 0) {
-        float* dst = a.relw_g + (bh * a.N + t) * W;
+      if (half == 0) {
+        // every row of the tile is written (rows past N hold the finite values of the clamped token: kernel B masks
+        // them through its -inf row bias but must not meet uninitialised memory)
+        float* dst = a.relw_g + (bh * gridDim.x + blockIdx.x) * static_cast<size_t>(W) * AB_BM;
         if constexpr (W % 4 == 0) {
 #pragma unroll
           for (int j = 0; j < W / 4; ++j)
-            reinterpret_cast<float4*>(dst)[j] = make_float4(relw[4 * j], relw[4 * j + 1], relw[4 * j + 2], relw[4 * j + 3]);
+            reinterpret_cast<float4*>(dst)[j * AB_BM + row] =
+                make_float4(relw[4 * j], relw[4 * j + 1], relw[4 * j + 2], relw[4 * j + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < W; ++j) dst[j] = relw[j];
+          for (int j = 0; j < W; ++j) dst[j * AB_BM + row] = relw[j];
         }
       }
     }
@@ -374,16 +472,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       tc_fence_before();
       asm volatile("bar.sync 1, %0;" ::"n"(AB_SMX) : "memory");
-      // coalesced copy of the rel_h rows to global (kernel B reads them): warp per row.  It finishes before the
-      // arrive below, i.e. before any thread can start overwriting rel_h rows with Gh' (first bar_s needs all arrivals)
+      // rel_h rows to global for kernel B, row-innermost: each thread copies its own row (the two column halves take
+      // alternate image rows): smem reads at stride h+1 floats (odd: conflict-free), global stores of 128 contiguous
+      // bytes per warp.  It finishes before the arrive below, i.e. before any thread can start overwriting rel_h rows
+      // with Gh' (first bar_s needs all arrivals)
       {
-        const int rows_valid = min(AB_BM, a.N - q0);
-        float* dst = a.relh_g + (bh * a.N + q0) * h;
-        for (int r = warp; r < rows_valid; r += AB_SMX / 32)
-          for (int i = lane; i < h; i += 32) dst[static_cast<size_t>(r) * h + i] = relh_gen[static_cast<size_t>(r) * ldr + i];
+        float* dst = a.relh_g + (bh * gridDim.x + blockIdx.x) * static_cast<size_t>(h) * AB_BM + row;
+        for (int i = half; i < h; i += 2) dst[static_cast<size_t>(i) * AB_BM] = my_relh[i];
       }
       __syncwarp();
       mbar_arrive(bar_gr);
+    }
     }
     if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 3);
     // Per-score arithmetic on packed fp32 pairs (FFMA2 / FADD2 / FMUL2) when W is even (a pair of adjacent keys then
@@ -489,6 +588,110 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 
     if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 4);
+    __nv_bfloat16* qrow = a.dqkv + (static_cast<size_t>(b) * a.N + t) * (3 * C) + head * 64 + half * 32;
+    if (merged_ep) {
+      // ---------------- single-phase epilogue ----------------
+      // Gw' totals of the two column halves through the dO tile (dead once the main loop has retired; row stride W+1
+      // floats: conflict-free), then both Toeplitz operands x 8 as bf16 16-byte chunks: Gh^ -> dS buffer 0, Gw^ ->
+      // dS buffer 1 (dS is stored unscaled: the accumulator holds 8 * dQ_bias + dS.K, the read-out multiplies by 1/8)
+      mbar_wait(bar_e, 0);
+      tc_fence_after();
+      float* xch = reinterpret_cast<float*>(gen + A_SDO) + static_cast<size_t>(row) * (W + 1);
+      if (half == 1) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) xch[j] = gw[j];
+      }
+      for (int c0 = half * 8; c0 < a.th_pad; c0 += 16) {
+        float g[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int i = i_r + (h - 1) - (c0 + c);
+          g[c] = (i >= 0 && i < h) ? my_gh[i] * 8.0f : 0.f;
+        }
+        const uint32_t addr = sdS + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+        st_shared_v4(addr, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                     pack_bf16x2(g[6], g[7]));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(AB_SMX) : "memory");
+      if (half == 0) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) xch[j] += gw[j];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(AB_SMX) : "memory");
+      for (int c0 = half * 8; c0 < a.tw_pad; c0 += 16) {
+        float g[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int j = j_r + (W - 1) - (c0 + c);
+          g[c] = (j >= 0 && j < W) ? xch[j] * 8.0f : 0.f;
+        }
+        const uint32_t addr = sdS + 32768 + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+        st_shared_v4(addr, pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                     pack_bf16x2(g[6], g[7]));
+      }
+      // the dT MMAs read 128 operand columns (M = 128) of each buffer: zero what lies beyond th_pad / tw_pad
+      for (int c0 = a.th_pad + half * 8; c0 < 128; c0 += 16) {
+        const uint32_t addr = sdS + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+        st_shared_v4(addr, 0u, 0u, 0u, 0u);
+      }
+      for (int c0 = a.tw_pad + half * 8; c0 < 128; c0 += 16) {
+        const uint32_t addr = sdS + 32768 + (c0 >> 6) * 16384 + row * 128 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+        st_shared_v4(addr, 0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_er);
+      if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 5);
+      // ---------------- read-out: dT_h / dT_w partials, dQ -> bf16 (each half owns 32 of the 64 columns) ----------
+      mbar_wait(bar_e2, 0);
+      tc_fence_after();
+      if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 6);
+      for (int mh = 0; mh * 128 < a.th_pad; ++mh) {
+        const int tt = mh * 128 + row;
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tS + lane_addr + mh * 64 + half * 32 + c0, v);
+          tmem_wait_ld();
+          if (tt < 2 * h - 1) {
+            float* dst = ws_cta + static_cast<size_t>(half * 32 + c0) * ws_rows + tt;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) dst[static_cast<size_t>(q) * ws_rows] = __uint_as_float(v[q]) * 0.125f;
+          }
+        }
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tS + lane_addr + 128 + half * 32 + c0, v);
+        tmem_wait_ld();
+        if (row < 2 * W - 1) {
+          float* dst = ws_cta + static_cast<size_t>(half * 32 + c0) * ws_rows + (2 * h - 1 + row);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) dst[static_cast<size_t>(q) * ws_rows] = __uint_as_float(v[q]) * 0.125f;
+        }
+      }
+      mbar_wait(bar_e, 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld_x16(tdQ + lane_addr + half * 32 + c0, o);
+        tmem_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[q * 8 + 0]) * 0.125f, __uint_as_float(o[q * 8 + 1]) * 0.125f);
+            u.y = pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * 0.125f, __uint_as_float(o[q * 8 + 3]) * 0.125f);
+            u.z = pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * 0.125f, __uint_as_float(o[q * 8 + 5]) * 0.125f);
+            u.w = pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * 0.125f, __uint_as_float(o[q * 8 + 7]) * 0.125f);
+            *reinterpret_cast<uint4*>(qrow + c0 + q * 8) = u;
+          }
+        }
+      }
+      if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 7);
+    } else {
     // ---------------- epilogue phase 1: Gh^ x 8 (bf16, K-major / MN-major dual view) ----------------
     // (dS is stored unscaled, so the accumulator holds 8 * dQ_bias + dS.K; the final read-out multiplies by 1/8)
     mbar_wait(bar_e, 0);
@@ -519,11 +722,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_x16(tS + lane_addr + mh * 64 + half * 32 + c0, v);
         tmem_wait_ld();
         if (tt < 2 * h - 1) {
-          float4* dst = reinterpret_cast<float4*>(ws_cta + static_cast<size_t>(tt) * 64 + half * 32 + c0);
+          float* dst = ws_cta + static_cast<size_t>(half * 32 + c0) * ws_rows + tt;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            dst[q] = make_float4(__uint_as_float(v[4 * q]) * 0.125f, __uint_as_float(v[4 * q + 1]) * 0.125f,
-                                 __uint_as_float(v[4 * q + 2]) * 0.125f, __uint_as_float(v[4 * q + 3]) * 0.125f);
+          for (int q = 0; q < 16; ++q) dst[static_cast<size_t>(q) * ws_rows] = __uint_as_float(v[q]) * 0.125f;
         }
       }
     }
@@ -573,14 +774,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_x16(tS + lane_addr + half * 32 + c0, v);
       tmem_wait_ld();
       if (row < 2 * W - 1) {
-        float4* dst = reinterpret_cast<float4*>(ws_cta + static_cast<size_t>(2 * h - 1 + row) * 64 + half * 32 + c0);
+        float* dst = ws_cta + static_cast<size_t>(half * 32 + c0) * ws_rows + (2 * h - 1 + row);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_float4(__uint_as_float(v[4 * q]) * 0.125f, __uint_as_float(v[4 * q + 1]) * 0.125f,
-                               __uint_as_float(v[4 * q + 2]) * 0.125f, __uint_as_float(v[4 * q + 3]) * 0.125f);
+        for (int q = 0; q < 16; ++q) dst[static_cast<size_t>(q) * ws_rows] = __uint_as_float(v[q]) * 0.125f;
       }
     }
-    __nv_bfloat16* qrow = a.dqkv + (static_cast<size_t>(b) * a.N + t) * (3 * C) + head * 64 + half * 32;
 #pragma unroll
     for (int c0 = 0; c0 < 32; c0 += 16) {
       uint32_t o[16];
@@ -599,6 +797,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     if (row == 0 && half == 0) AB_TRACE(0, 1, 15, 7);
+    }
   }
 
   tc_fence_before();
@@ -791,22 +990,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (!valid_n) t = a.N - 1;
       lse_n = a.lse[bh * a.N + t];
       delta_n = a.delta[bh * a.N + t];
-      const float* ph = a.relh_g + (bh * a.N + t) * h;
+      // row-innermost tiles written by kernel A: coalesced (128 B per warp for rel_h, 512 B per warp for rel_w)
+      const float* ph = a.relh_g + (bh * num_q + i) * static_cast<size_t>(h) * AB_BM + row;
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
         const int ii = jt * R + half * RH + r;
-        hb_n[r] = ph[ii < h ? ii : h - 1];
+        hb_n[r] = ph[static_cast<size_t>(ii < h ? ii : h - 1) * AB_BM];
       }
-      const float* pw = a.relw_g + (bh * a.N + t) * W;
+      const float* pw = a.relw_g + (bh * num_q + i) * static_cast<size_t>(W) * AB_BM;
       if constexpr (W % 4 == 0) {
 #pragma unroll
         for (int j = 0; j < W / 4; ++j) {
-          const float4 q4 = reinterpret_cast<const float4*>(pw)[j];
+          const float4 q4 = reinterpret_cast<const float4*>(pw)[j * AB_BM + row];
           relw_n[4 * j] = q4.x; relw_n[4 * j + 1] = q4.y; relw_n[4 * j + 2] = q4.z; relw_n[4 * j + 3] = q4.w;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < W; ++j) relw_n[j] = pw[j];
+        for (int j = 0; j < W; ++j) relw_n[j] = pw[j * AB_BM + row];
       }
     };
     fetch(0);
@@ -969,7 +1169,8 @@ extern "C" void pk_attn_bwd_debug(int flags) { g_attnb_debug = flags; }
 extern "C" void pk_attn_bwd_set_trace(void* buf) { g_attnb_trace = static_cast<long long*>(buf); }
 
 // qkv / dqkv: bf16 [B*N, 3C];  O, dO: bf16 [B*N, C];  lse: fp32 [B*heads, N] from pk_attn_fwd
-// scratch buffers (caller-allocated): delta [B*heads*N], relh_g [B*heads*N*h], relw_g [B*heads*N*w] fp32
+// scratch buffers (caller-allocated): delta [B*heads*N], relh_g [B*heads*Np*h], relw_g [B*heads*Np*w] fp32 with
+// Np = N rounded up to a multiple of 128 (whole query tiles, row-innermost: see AttnBwdArgs)
 // dt_ws: pk_attn_bwd_ws_floats(B, heads, h, w) fp32 (per-CTA partial table gradients)
 // dTh [2h-1, 64], dTw [2w-1, 64]: fp32, ADDED to (caller zero-initialises or passes a running gradient)
 extern "C" long long pk_attn_bwd_ws_floats(int B, int heads, int h, int w) {
@@ -977,37 +1178,43 @@ extern "C" long long pk_attn_bwd_ws_floats(int B, int heads, int h, int w) {
   return ctas * (2 * h - 1 + 2 * w - 1) * 64;
 }
 
-// dT[r][c] += sum over CTA slices ws[cta][r][c].  grid (rows, DT_STRIPES), block (64, 16): the slices are strided
-// over blockIdx.y / threadIdx.y, four loads in flight per thread, smem tree over threadIdx.y, one atomic per
-// (row, column, stripe).
+// dT[r][c] += sum over CTA slices ws[cta][c][r] (table row innermost).  grid (64 columns, DT_STRIPES, row chunks), block
+// (DT_RX, DT_RY): threadIdx.x walks the table rows (coalesced), the slices are strided over blockIdx.y / threadIdx.y
+// with four loads in flight per thread, smem tree over threadIdx.y, one atomic per (row, column, stripe).
 constexpr int DT_STRIPES = 4;
-__global__ void __launch_bounds__(1024)
+constexpr int DT_RX = 64, DT_RY = 16;
+__global__ void __launch_bounds__(DT_RX * DT_RY)
 attn_dt_reduce_kernel(const float* __restrict__ ws, int nctas, int rows, int rows_h, float* __restrict__ dTh,
                       float* __restrict__ dTw) {
-  __shared__ float red[16][64];
+  __shared__ float red[DT_RY][DT_RX];
   pdl_launch_dependents();
   pdl_wait();
-  const int r = blockIdx.x, c = threadIdx.x;
+  const int c = blockIdx.x;
   const size_t slice = static_cast<size_t>(rows) * 64;
-  const float* p = ws + static_cast<size_t>(r) * 64 + c;
-  const int step = DT_STRIPES * 16;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int i = blockIdx.y * 16 + threadIdx.y;
-  for (; i + 3 * step < nctas; i += 4 * step) {
-    s0 += p[static_cast<size_t>(i) * slice];
-    s1 += p[static_cast<size_t>(i + step) * slice];
-    s2 += p[static_cast<size_t>(i + 2 * step) * slice];
-    s3 += p[static_cast<size_t>(i + 3 * step) * slice];
-  }
-  for (; i < nctas; i += step) s0 += p[static_cast<size_t>(i) * slice];
-  red[threadIdx.y][c] = (s0 + s1) + (s2 + s3);
-  __syncthreads();
-  if (threadIdx.y == 0) {
-    float s = 0.f;
+  const int step = DT_STRIPES * DT_RY;
+  {
+    const int r = blockIdx.z * DT_RX + threadIdx.x;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (r < rows) {
+      const float* p = ws + static_cast<size_t>(c) * rows + r;
+      int i = blockIdx.y * DT_RY + threadIdx.y;
+      for (; i + 3 * step < nctas; i += 4 * step) {
+        s0 += p[static_cast<size_t>(i) * slice];
+        s1 += p[static_cast<size_t>(i + step) * slice];
+        s2 += p[static_cast<size_t>(i + 2 * step) * slice];
+        s3 += p[static_cast<size_t>(i + 3 * step) * slice];
+      }
+      for (; i < nctas; i += step) s0 += p[static_cast<size_t>(i) * slice];
+    }
+    red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.y == 0 && r < rows) {
+      float s = 0.f;
 #pragma unroll
-    for (int y = 0; y < 16; ++y) s += red[y][c];
-    float* dst = r < rows_h ? dTh + static_cast<size_t>(r) * 64 + c : dTw + static_cast<size_t>(r - rows_h) * 64 + c;
-    atomicAdd(dst, s);
+      for (int y = 0; y < DT_RY; ++y) s += red[y][threadIdx.x];
+      float* dst = r < rows_h ? dTh + static_cast<size_t>(r) * 64 + c : dTw + static_cast<size_t>(r - rows_h) * 64 + c;
+      atomicAdd(dst, s);
+    }
   }
 }
 
@@ -1041,10 +1248,31 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __re
   }
 }
 
+static int attn_bwd_impl(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
+                         const void* tw, void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g,
+                         float* relw_g, float* dt_ws, int B, int heads, int h, int w, int th_pad, int tw_pad,
+                         int rel_ready, void* stream);
+
 extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
                            const void* tw, void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g,
                            float* relw_g, float* dt_ws, int B, int heads, int h, int w, int th_pad, int tw_pad,
                            void* stream) {
+  return attn_bwd_impl(qkv, O, dO, lse, th, tw, dqkv, dTh, dTw, delta, relh_g, relw_g, dt_ws, B, heads, h, w, th_pad,
+                       tw_pad, 0, stream);
+}
+// relh_g / relw_g are INPUTS here: the bias rows stored by pk_attn_fwd_save on the same qkv / tables
+extern "C" int pk_attn_bwd_saved(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
+                                 const void* tw, void* dqkv, float* dTh, float* dTw, float* delta,
+                                 const float* relh_g, const float* relw_g, float* dt_ws, int B, int heads, int h, int w,
+                                 int th_pad, int tw_pad, void* stream) {
+  return attn_bwd_impl(qkv, O, dO, lse, th, tw, dqkv, dTh, dTw, delta, const_cast<float*>(relh_g),
+                       const_cast<float*>(relw_g), dt_ws, B, heads, h, w, th_pad, tw_pad, 1, stream);
+}
+
+static int attn_bwd_impl(const void* qkv, const void* O, const void* dO, const float* lse, const void* th,
+                         const void* tw, void* dqkv, float* dTh, float* dTw, float* delta, float* relh_g,
+                         float* relw_g, float* dt_ws, int B, int heads, int h, int w, int th_pad, int tw_pad,
+                         int rel_ready, void* stream) {
   PK_CHECK(qkv && O && dO && lse && th && tw && dqkv && dTh && dTw && delta && relh_g && relw_g && dt_ws,
            "pk_attn_bwd: null pointer");
   PK_CHECK(th_pad % 16 == 0 && tw_pad % 16 == 0 && th_pad >= 2 * h - 1 && tw_pad >= 2 * w - 1 &&
@@ -1064,6 +1292,7 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   a.lse = lse; a.delta = delta; a.relh_g = relh_g; a.relw_g = relw_g;
   a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   a.dt_ws = dt_ws;
+  a.rel_ready = rel_ready;
   a.trace = g_attnb_trace;
   a.debug = g_attnb_debug;
 
@@ -1129,7 +1358,7 @@ extern "C" int pk_attn_bwd(const void* qkv, const void* O, const void* dO, const
   {
     const int rows = 2 * h - 1 + 2 * w - 1;
     const int nctas = static_cast<int>(gridA.x * gridA.y * gridA.z);
-    launch_pdl(attn_dt_reduce_kernel, dim3(rows, DT_STRIPES), dim3(64, 16), 0, st, static_cast<const float*>(dt_ws),
+    launch_pdl(attn_dt_reduce_kernel, dim3(64, DT_STRIPES, (rows + DT_RX - 1) / DT_RX), dim3(DT_RX, DT_RY), 0, st, static_cast<const float*>(dt_ws),
                nctas, rows, 2 * h - 1, dTh, dTw);
     PK_LAUNCH_CHECK("pk_attn_bwd(dT reduce)");
   }

@@ -29,6 +29,14 @@ constexpr int ATT_BM = 128;
 constexpr int ATT_KT = 112;
 constexpr int ATT_THREADS = 192;
 constexpr float LOG2E = 1.4426950408889634f;
+// PK_ATTN_FWD_TS: 0 = P through shared memory (SS form); 1 (default) = P in TMEM, S(j+1) issued after P(j).V(j);
+// 2 = P in TMEM and S(j+1) issued BEFORE P(j).V(j), so that the next tile's scores do not wait behind the seven P.V
+// MMAs (~390 cycles of a CTA's ~2650-cycle tile chain, profiles/r02_attn_cta_timelines.txt): P(j+1) then starts being
+// written while P(j).V(j) may still read P(j), so the 16-key P chunks rotate through ten 8-column TMEM slots (tile j's
+// chunk c lives in slot (7 j + c) mod 10: the first three chunks of a tile land in free slots, the fourth waits for
+// the previous tile's P.V to retire).  Correct (same tests green) but SLOWER on the B200 at the B = 8 geometry:
+// 0.171 ms against 0.161 ms - the two co-resident CTAs' softmax phases then overlap and a tile's softmax pass
+// stretches from ~1370 to ~1650 cycles: the SM's softmax throughput, not the per-CTA chain, is the bound.
 #ifndef PK_ATTN_FWD_TS
 #define PK_ATTN_FWD_TS 1
 #endif
@@ -48,6 +56,12 @@ struct AttnFwdArgs {
   __nv_bfloat16* out;     // [B*N, ldo]
   int ldo;
   float* lse;             // [B*heads, N]  (log2 domain: m + log2(l))
+  // optional (training): the log2e-scaled bias rows rel_h / rel_w of every query, kept for the backward kernels, which
+  // then start from two coalesced loads instead of recomputing G_h / G_w on the tensor cores and re-doing the Toeplitz
+  // gathers (that prologue was 10 k of a dQ CTA's 48 k cycles).  Layout: per 128-query tile, query row innermost
+  // (attention_bwd.cu AttnBwdArgs): relh [B*heads, q tiles, h, 128], relw [B*heads, q tiles, W/4, 128] float4.
+  float* relh_out;
+  float* relw_out;
   long long* trace;       // optional debug timeline (CTA 0 only): [role][tile][event] clock64 stamps
 };
 
@@ -109,10 +123,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
-  // TMEM columns (256 per CTA, two CTAs per SM): S [0,112) | O [128,192) | P as packed bf16 pairs [192,248)
-  const uint32_t tS = tmem, tO = tmem + 128;
+  // TMEM columns (256 per CTA, two CTAs per SM): S [0,112) | O [112,176) | P as packed bf16 pairs: ten 8-column
+  // slots [176,256) (PK_ATTN_FWD_TS=1 uses the first seven in place)
+  const uint32_t tS = tmem, tO = tmem + 112;
 #if PK_ATTN_FWD_TS
-  const uint32_t tP = tmem + 192;
+  const uint32_t tP = tmem + 176;
 #endif
   pdl_launch_dependents();   // programmatic dependent launch (host_common.h): the prologue above overlaps the
   pdl_wait();                // previous kernel's tail; nothing before this line touches global memory
@@ -185,6 +200,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         dp[kk] = make_sdesc(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
         dv[kk] = make_sdesc(sV + kk * 2048, 16, 1024);
       }
+#if PK_ATTN_FWD_TS == 2
+      // S(0), then per tile: [P(j) ready] -> S(j+1) -> P(j).V(j)
+      mbar_wait(bar_kf, 0);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tS, dq[k], dk[k], idesc_qk, k != 0);
+        umma_commit(bar_ke);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+      for (int j = 0; j < num_tiles; ++j) {
+        ATT_TRACE(1, j, 0);
+        mbar_wait(bar_p, j & 1);      // softmax(j) done: S is free, P(j) sits in its TMEM slots
+        ATT_TRACE(1, j, 4);
+        if (j + 1 < num_tiles) {
+          mbar_wait(bar_kf, (j + 1) & 1);
+          ATT_TRACE(1, j, 1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(tS, dq[k], dk[k], idesc_qk, k != 0);
+            umma_commit(bar_ke);
+            umma_commit(bar_s);
+          }
+          __syncwarp();
+          ATT_TRACE(1, j, 2);
+        }
+        mbar_wait(bar_vf, j & 1);
+        ATT_TRACE(1, j, 3);
+        tc_fence_after();
+        const int slot0 = (7 * j) % 10;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < ATT_KT / 16; ++kk) {
+            int sl = slot0 + kk;
+            if (sl >= 10) sl -= 10;
+            umma_ts(tO, tP + sl * 8, dv[kk], idesc_pv, (j | kk) != 0);
+          }
+          umma_commit(bar_ve);
+          if (j == num_tiles - 1) umma_commit(bar_o);
+        }
+        __syncwarp();
+      }
+#else
       for (int j = 0; j < num_tiles; ++j) {
         ATT_TRACE(1, j, 0);
         mbar_wait(bar_kf, j & 1);
@@ -217,6 +277,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         __syncwarp();
       }
+#endif
     }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
@@ -252,6 +313,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       mbar_arrive(bar_gr);
+      if (a.relw_out != nullptr) {
+        float* dst = a.relw_out + ((static_cast<size_t>(b) * a.heads + head) * gridDim.x + blockIdx.x) *
+                                      static_cast<size_t>(W) * ATT_BM;
+        if constexpr (W % 4 == 0) {
+#pragma unroll
+          for (int j = 0; j < W / 4; ++j)
+            reinterpret_cast<float4*>(dst)[j * ATT_BM + row] =
+                make_float4(relw[4 * j], relw[4 * j + 1], relw[4 * j + 2], relw[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < W; ++j) dst[j * ATT_BM + row] = relw[j];
+        }
+      }
     }
     // ---- rel_h -> smem [row][h]  (Toeplitz gather: rel_h[i] = G_h[i_r - i + h - 1]) ----
     {
@@ -270,6 +344,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       mbar_arrive(bar_gr);
+      if (a.relh_out != nullptr) {
+        // rows past N carry the (finite) values of the clamped token: the backward masks them but reads them
+        float* dst = a.relh_out + ((static_cast<size_t>(b) * a.heads + head) * gridDim.x + blockIdx.x) *
+                                      static_cast<size_t>(h) * ATT_BM + row;
+        for (int i = 0; i < h; ++i) dst[static_cast<size_t>(i) * ATT_BM] = my_relh[i];
+      }
     }
 
     float m_ref = -INFINITY, l_sum = 0.f;
@@ -281,6 +361,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int i = j * R + r;
         hb[r] = i < h ? my_relh[i] : -INFINITY;   // image rows past the end: bias -inf -> p = 0, no per-score select
       }
+#if PK_ATTN_FWD_TS == 2
+      const int pslot0 = (7 * j) % 10;
+#endif
       if (row == 0) ATT_TRACE(2, j, 0);
       mbar_wait(bar_s, j & 1);
       if (row == 0) ATT_TRACE(2, j, 1);
@@ -360,7 +443,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t pk8[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) pk8[q] = pack_bf16x2(p[2 * q], p[2 * q + 1]);
+#if PK_ATTN_FWD_TS == 2
+            // chunk ci of tile j -> slot (7 j + ci) mod 10; from the fourth chunk on the slot was last read by the
+            // previous tile's P.V MMAs, which must have retired (the first three slots are free by construction)
+            if (ci == 3 && j >= 1) {
+              mbar_wait(bar_ve, (j - 1) & 1);
+              tc_fence_after();
+            }
+            int sl = pslot0 + ci;
+            if (sl >= 10) sl -= 10;
+            tmem_st_x8(tP + lane_addr + sl * 8, pk8);
+#else
             tmem_st_x8(tP + lane_addr + (c0 >> 1), pk8);
+#endif
           }
 #else
           // 16 consecutive keys = two 16-byte chunks of this row inside K-block (c0 / 64)
@@ -387,6 +482,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           break;
         }
         // rescale the running state to the new reference point and redo the tile
+#if PK_ATTN_FWD_TS == 2
+        if (j >= 1) {   // S(j) was issued ahead of P(j-1).V(j-1): O is only stable once that has retired
+          mbar_wait(bar_ve, (j - 1) & 1);
+          tc_fence_after();
+        }
+#endif
         float alpha = 1.0f;
         if (grow) {
           alpha = fast_exp2(-mx);
@@ -458,8 +559,23 @@ extern "C" void pk_attn_set_trace(void* buf) { g_attn_trace = static_cast<long l
 
 // qkv: bf16 [B*N, 3C] (columns (3, head, 64) as produced by the qkv Linear, models_painter.py:76-78)
 // th / tw: bf16 rel-pos tables, zero-padded to th_pad / tw_pad rows (multiples of 16), [rows, 64]
+static int attn_fwd_impl(const void* qkv, const void* th, const void* tw, void* out, float* lse, float* relh_out,
+                         float* relw_out, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream);
+
 extern "C" int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void* out, float* lse, int B,
                            int heads, int h, int w, int th_pad, int tw_pad, void* stream) {
+  return attn_fwd_impl(qkv, th, tw, out, lse, nullptr, nullptr, B, heads, h, w, th_pad, tw_pad, stream);
+}
+// training forward: additionally stores every query's bias rows (relh_g / relw_g: B*heads*Np*h resp. *w floats,
+// Np = N rounded up to 128) for pk_attn_bwd_saved
+extern "C" int pk_attn_fwd_save(const void* qkv, const void* th, const void* tw, void* out, float* lse, float* relh_g,
+                                float* relw_g, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream) {
+  PK_CHECK(lse && relh_g && relw_g, "pk_attn_fwd_save: null pointer");
+  return attn_fwd_impl(qkv, th, tw, out, lse, relh_g, relw_g, B, heads, h, w, th_pad, tw_pad, stream);
+}
+
+static int attn_fwd_impl(const void* qkv, const void* th, const void* tw, void* out, float* lse, float* relh_out,
+                         float* relw_out, int B, int heads, int h, int w, int th_pad, int tw_pad, void* stream) {
   PK_CHECK(qkv && th && tw && out, "pk_attn_fwd: null pointer");
   PK_CHECK(B > 0 && heads > 0 && h > 0 && w > 0, "pk_attn_fwd: bad shape");
   PK_CHECK(th_pad % 16 == 0 && tw_pad % 16 == 0 && th_pad >= 2 * h - 1 && tw_pad >= 2 * w - 1 &&
@@ -480,6 +596,8 @@ extern "C" int pk_attn_fwd(const void* qkv, const void* th, const void* tw, void
   a.out = static_cast<__nv_bfloat16*>(out);
   a.ldo = C;
   a.lse = lse;
+  a.relh_out = relh_out;
+  a.relw_out = relw_out;
   a.trace = g_attn_trace;
 
   CUtensorMap tmQ, tmKV, tmTh, tmTw;

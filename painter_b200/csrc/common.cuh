@@ -356,6 +356,43 @@ __device__ __forceinline__ f32x2 mul_f2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// The GEMM-epilogue GELU / GELU' on a PAIR of activations: the same operations in the same order as gelu_fast /
+// gelu_fast_grad (bit-identical results), with the polynomial and the products on packed fp32 pairs - 10 resp. 16
+// issue slots per pair instead of 16 resp. 28 (the fc1 / fc2-dgrad epilogues are what bounds those GEMMs).
+__device__ __forceinline__ f32x2 gelu_clamped_sq(f32x2 x2) {
+  float u0, u1;
+  unpack_f2(mul_f2(x2, x2), u0, u1);
+  return pack_f2(fminf(u0, 64.0f), fminf(u1, 64.0f));
+}
+__device__ __forceinline__ void gelu_fast_pair(float x0, float x1, float& g0, float& g1) {
+  const f32x2 x2 = pack_f2(x0, x1);
+  const f32x2 u2 = gelu_clamped_sq(x2);
+  const f32x2 p2 = fma_f2(fma_f2(pack_f2(GELU_P2, GELU_P2), u2, pack_f2(GELU_P1, GELU_P1)), u2,
+                          pack_f2(GELU_P0, GELU_P0));
+  float a0, a1;
+  unpack_f2(mul_f2(x2, p2), a0, a1);
+  const f32x2 t2 = pack_f2(tanh_approx(a0), tanh_approx(a1));
+  const f32x2 hx2 = mul_f2(pack_f2(0.5f, 0.5f), x2);
+  unpack_f2(fma_f2(hx2, t2, hx2), g0, g1);
+}
+// (d0, d1) = (y0 * gelu'(x0), y1 * gelu'(x1))
+__device__ __forceinline__ void gelu_fast_grad_mul_pair(float x0, float x1, float y0, float y1, float& d0, float& d1) {
+  const f32x2 x2 = pack_f2(x0, x1);
+  const f32x2 u2 = gelu_clamped_sq(x2);
+  const f32x2 p2 = fma_f2(fma_f2(pack_f2(GELU_P2, GELU_P2), u2, pack_f2(GELU_P1, GELU_P1)), u2,
+                          pack_f2(GELU_P0, GELU_P0));
+  const f32x2 q2 = fma_f2(fma_f2(pack_f2(5.0f * GELU_P2, 5.0f * GELU_P2), u2, pack_f2(3.0f * GELU_P1, 3.0f * GELU_P1)),
+                          u2, pack_f2(GELU_P0, GELU_P0));
+  float a0, a1;
+  unpack_f2(mul_f2(x2, p2), a0, a1);
+  const float t0 = tanh_approx(a0), t1 = tanh_approx(a1);
+  const f32x2 t2 = pack_f2(t0, t1);
+  const f32x2 s2 = fma_f2(pack_f2(-t0, -t1), t2, pack_f2(1.0f, 1.0f));
+  const f32x2 hxs2 = mul_f2(mul_f2(pack_f2(0.5f, 0.5f), x2), s2);
+  const f32x2 g2 = fma_f2(hxs2, q2, fma_f2(pack_f2(0.5f, 0.5f), t2, pack_f2(0.5f, 0.5f)));
+  unpack_f2(mul_f2(pack_f2(y0, y1), g2), d0, d1);
+}
+
 // exp2 of a pair of scores.  Where a softmax pass is bound by the MUFU pipe (16 ex2 / clk / SM) rather than by issue
 // slots, a compile-time fraction of the pairs (mask: one bit per pair position modulo 4) is evaluated on the FMA / ALU
 // pipes instead (measured, B = 8 geometry, scripts/attn_poly_sweep.sh: the first pass of the dK/dV kernel - which does

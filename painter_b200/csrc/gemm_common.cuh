@@ -366,7 +366,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
     for (int it = 0; it < 8; ++it) {
       zb[it] = pack4_bf16(xs[it]);
       const float4 zr = unpack4_bf16(zb[it]);
-      hb[it] = pack4_bf16(make_float4(gelu_fast(zr.x), gelu_fast(zr.y), gelu_fast(zr.z), gelu_fast(zr.w)));
+      float4 g;
+      gelu_fast_pair(zr.x, zr.y, g.x, g.y);
+      gelu_fast_pair(zr.z, zr.w, g.z, g.w);
+      hb[it] = pack4_bf16(g);
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -381,8 +384,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const PkEpilogue& e, float* 
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const float4 z = unpack4_bf16(auxh[it]);
-      o[it] = pack4_bf16(make_float4(xs[it].x * gelu_fast_grad(z.x), xs[it].y * gelu_fast_grad(z.y),
-                                     xs[it].z * gelu_fast_grad(z.z), xs[it].w * gelu_fast_grad(z.w)));
+      float4 d;
+      gelu_fast_grad_mul_pair(z.x, z.y, xs[it].x, xs[it].y, d.x, d.y);
+      gelu_fast_grad_mul_pair(z.z, z.w, xs[it].z, xs[it].w, d.z, d.w);
+      o[it] = pack4_bf16(d);
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {

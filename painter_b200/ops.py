@@ -104,22 +104,32 @@ def relpos_table_bf16(table):
     return out
 
 
-def attn_fwd(qkv, th, tw, B, heads, h, w, need_lse=True):
+def attn_fwd(qkv, th, tw, B, heads, h, w, need_lse=True, save_rel=False):
     """Fused attention forward. qkv: bf16 [B*h*w, 3*heads*64]; th/tw: padded bf16 tables for an (h, w) grid.
-    Returns (out bf16 [B*h*w, heads*64], lse fp32 [B*heads, h*w] in the log2 domain)."""
+    Returns (out bf16 [B*h*w, heads*64], lse fp32 [B*heads, h*w] in the log2 domain); with save_rel=True (training) a
+    third value: the (relh, relw) bias-row buffers the forward keeps for `attn_bwd(..., rel=...)`."""
     _req(qkv, torch.bfloat16, "qkv")
     N, C = h * w, heads * 64
     assert qkv.is_contiguous() and tuple(qkv.shape) == (B * N, 3 * C)
     assert th.shape[0] >= 2 * h - 1 and tw.shape[0] >= 2 * w - 1
     out = torch.empty((B * N, C), dtype=torch.bfloat16, device=qkv.device)
-    lse = torch.empty((B * heads, N), dtype=torch.float32, device=qkv.device) if need_lse else None
+    lse = torch.empty((B * heads, N), dtype=torch.float32, device=qkv.device) if (need_lse or save_rel) else None
+    if save_rel:
+        Np = (N + 127) // 128 * 128     # whole 128-query tiles, query row innermost
+        relh = torch.empty((B * heads * Np * h,), dtype=torch.float32, device=qkv.device)
+        relw = torch.empty((B * heads * Np * w,), dtype=torch.float32, device=qkv.device)
+        check(lib().pk_attn_fwd_save(_ptr(qkv), _ptr(th), _ptr(tw), _ptr(out), _ptr(lse), _ptr(relh), _ptr(relw),
+                                     B, heads, h, w, th.shape[0], tw.shape[0], _stream()), "pk_attn_fwd_save")
+        return out, lse, (relh, relw)
     check(lib().pk_attn_fwd(_ptr(qkv), _ptr(th), _ptr(tw), _ptr(out), _ptr(lse), B, heads, h, w,
                             th.shape[0], tw.shape[0], _stream()), "pk_attn_fwd")
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None, dT_out=None):
-    """Fused attention backward.  Returns (dqkv bf16 [B*N, 3C], dTh fp32 [2h-1, 64], dTw fp32 [2w-1, 64])."""
+def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None, dT_out=None, rel=None):
+    """Fused attention backward.  Returns (dqkv bf16 [B*N, 3C], dTh fp32 [2h-1, 64], dTw fp32 [2w-1, 64]).
+    rel: the (relh, relw) buffers of `attn_fwd(..., save_rel=True)` on the same operands (the dQ kernel then loads its
+    bias rows instead of recomputing them)."""
     N, C = h * w, heads * 64
     _req(dout, torch.bfloat16, "dout")
     assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
@@ -133,14 +143,24 @@ def attn_bwd(qkv, out, dout, lse, th, tw, B, heads, h, w, L_h=None, L_w=None, dT
         dTh = torch.zeros((2 * h - 1, 64), dtype=torch.float32, device=dev)
         dTw = torch.zeros((2 * w - 1, 64), dtype=torch.float32, device=dev)
     delta = torch.empty((B * heads * N,), dtype=torch.float32, device=dev)
-    relh_g = torch.empty((B * heads * N * h,), dtype=torch.float32, device=dev)
-    relw_g = torch.empty((B * heads * N * w,), dtype=torch.float32, device=dev)
+    Np = (N + 127) // 128 * 128     # the bias-row scratch is laid out in whole 128-query tiles
     L = lib()
     L.pk_attn_bwd_ws_floats.restype = ctypes.c_longlong
     dt_ws = torch.empty((int(L.pk_attn_bwd_ws_floats(B, heads, h, w)),), dtype=torch.float32, device=dev)
-    check(lib().pk_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(th), _ptr(tw), _ptr(dqkv),
-                            _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), _ptr(dt_ws), B, heads, h, w,
-                            th.shape[0], tw.shape[0], _stream()), "pk_attn_bwd")
+    if rel is not None:
+        relh_g, relw_g = rel
+        assert relh_g.numel() == B * heads * Np * h and relw_g.numel() == B * heads * Np * w
+        _req(relh_g, torch.float32, "relh")
+        _req(relw_g, torch.float32, "relw")
+        check(L.pk_attn_bwd_saved(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(th), _ptr(tw), _ptr(dqkv),
+                                  _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), _ptr(dt_ws), B, heads,
+                                  h, w, th.shape[0], tw.shape[0], _stream()), "pk_attn_bwd_saved")
+        return dqkv, dTh, dTw
+    relh_g = torch.empty((B * heads * Np * h,), dtype=torch.float32, device=dev)
+    relw_g = torch.empty((B * heads * Np * w,), dtype=torch.float32, device=dev)
+    check(L.pk_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(th), _ptr(tw), _ptr(dqkv),
+                        _ptr(dTh), _ptr(dTw), _ptr(delta), _ptr(relh_g), _ptr(relw_g), _ptr(dt_ws), B, heads, h, w,
+                        th.shape[0], tw.shape[0], _stream()), "pk_attn_bwd")
     return dqkv, dTh, dTw
 
 

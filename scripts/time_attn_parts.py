@@ -27,11 +27,14 @@ def timed(fn, iters=20):
 
 
 L = _lib.lib()
-res = {"fwd_ms": timed(lambda: ops.attn_fwd(qkv, th, tw, B, heads, h, w))}
-for name, flag in (("bwd_all", 0), ("bwd_no_dq", 4), ("bwd_no_dkv", 8), ("bwd_neither", 12)):
-    L.pk_attn_bwd_debug(flag)
-    res[name] = timed(lambda: ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w))
-L.pk_attn_bwd_debug(0)
-res["dq_ms"] = res["bwd_all"] - res["bwd_no_dq"]
-res["dkv_ms"] = res["bwd_all"] - res["bwd_no_dkv"]
+res = {"fwd_ms": timed(lambda: ops.attn_fwd(qkv, th, tw, B, heads, h, w)),
+       "fwd_save_ms": timed(lambda: ops.attn_fwd(qkv, th, tw, B, heads, h, w, save_rel=True))}
+_, _, rel = ops.attn_fwd(qkv, th, tw, B, heads, h, w, save_rel=True)
+for tag, r in (("", None), ("saved_", rel)):     # recomputed bias rows | bias rows kept by the forward
+    for name, flag in (("bwd_all", 0), ("bwd_no_dq", 4), ("bwd_no_dkv", 8), ("bwd_neither", 12)):
+        L.pk_attn_bwd_debug(flag)
+        res[tag + name] = timed(lambda: ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w, rel=r))
+    L.pk_attn_bwd_debug(0)
+    res[tag + "dq_ms"] = res[tag + "bwd_all"] - res[tag + "bwd_no_dq"]
+    res[tag + "dkv_ms"] = res[tag + "bwd_all"] - res[tag + "bwd_no_dkv"]
 print({k: round(v, 4) for k, v in res.items()})

@@ -28,14 +28,16 @@ for j in range(14):
     print(line)
 
 # ---- backward kernels ----
-out, lse = ops.attn_fwd(qkv, th, tw, B, heads, h, w)
+out, lse, rel = ops.attn_fwd(qkv, th, tw, B, heads, h, w, save_rel=True)
+if os.environ.get("PK_TRACE_RECOMPUTE"):
+    rel = None      # trace the pair that recomputes the bias rows in the dQ kernel
 do = (torch.randn(B * N, C, device="cuda") * 0.5).bfloat16()
 for _ in range(2):
-    ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w)
+    ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w, rel=rel)
 buf2 = torch.zeros(2 * 2 * 16 * 8, dtype=torch.int64, device="cuda")
 _lib.lib().pk_attn_bwd_debug(2 if os.environ.get("PK_TRACE_LAST") else 0)
 _lib.lib().pk_attn_bwd_set_trace(ctypes.c_void_p(buf2.data_ptr()))
-ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w)
+ops.attn_bwd(qkv, out, do, lse, th, tw, B, heads, h, w, rel=rel)
 torch.cuda.synchronize()
 _lib.lib().pk_attn_bwd_set_trace(None)
 _lib.lib().pk_attn_bwd_debug(0)

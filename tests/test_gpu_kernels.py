@@ -280,6 +280,15 @@ def test_attention_fwd_bwd_vs_reference_math(B, heads, h, w):
     for i in range(3):
         assert relmax(d[:, i], g[:, i]) < 2e-2, "qkv"[i]
     assert relmax(dTh, t32.grad[:2 * h - 1]) < 2e-2 and relmax(dTw, w32.grad[:2 * w - 1]) < 2e-2
+    # training pair: the forward keeps the bias rows, the dQ kernel loads them instead of recomputing them
+    out2, lse2, rel = ops.attn_fwd(qkv, th, tw, B, heads, h, w, save_rel=True)
+    assert torch.equal(out2, out) and torch.equal(lse2, lse)
+    dqkv2, dTh2, dTw2 = ops.attn_bwd(qkv, out2, dout, lse2, th, tw, B, heads, h, w, rel=rel)
+    d2 = dqkv2.float().reshape(B * N, 3, C)
+    for i in range(3):
+        assert relmax(d2[:, i], g[:, i]) < 2e-2, "saved " + "qkv"[i]
+        assert relmax(d2[:, i], d[:, i]) < 2e-3, "saved vs recomputed " + "qkv"[i]
+    assert relmax(dTh2, t32.grad[:2 * h - 1]) < 2e-2 and relmax(dTw2, w32.grad[:2 * w - 1]) < 2e-2
 
 
 @pytest.mark.parametrize("jump", [70.0, 1100.0])

@@ -123,3 +123,23 @@ def test_live_reference_stock_constructor_is_all_global():
     wbi = (list(range(0, 2)) + list(range(3, 5)) + list(range(6, 8)) + list(range(9, 11)) +
            list(range(12, 14)), list(range(15, 17)), list(range(18, 20)), list(range(21, 23)))
     assert not any(i in wbi for i in range(24))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (neither /root/reference nor baseline/_ref)")
+def test_live_reference_full_size_forward_pins_the_oracle_at_the_benchmark_geometry():
+    """The oracle against the UNMODIFIED reference module at the geometry the benchmark runs (ViT-L, 896x448, the stock
+    factory) - not only at the toy geometry of the golden vectors: eval-mode forward, B = 1, same seeded weights and
+    inputs, torch-CPU fp32 on both sides.  Loss within 1e-6 relative, logits within 1e-5 of their range."""
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    cfg = po.PainterConfig()
+    sd = synth_state_dict(cfg, 3)
+    imgs, tgts, mask, valid = synth_inputs(cfg, 1, 11)
+    model = ref_loader.models_painter().painter_vit_large_patch16_input896x448_win_dec64_8glb_sl1()
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        rl, rp, rm = model(imgs, tgts, bool_masked_pos=mask, valid=valid.clone())
+        ol, op, om = po.forward(sd, cfg, imgs, tgts, mask, valid)
+    assert abs(ol.item() - rl.item()) <= 1e-6 * abs(rl.item()), (ol.item(), rl.item())
+    assert _rel(op, rp) <= 1e-5, _rel(op, rp)
+    assert torch.equal(om, rm)
